@@ -1,0 +1,283 @@
+"""oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes front-end of the plain-C CPU restatement of twenty-first's hot path (oracle/oracle.c).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  The product (twenty-first_b200) never does.
+
+All arrays are numpy uint64 holding raw Montgomery words, i.e. the in-memory representation of
+the reference's BFieldElement (twenty-first/src/math/b_field_element.rs:84-86).
+
+Parity status: pinned against the reference's known-answer tests (tests/test_oracle_kat.py).
+The Rust reference itself cannot be built here (no cargo/rustc), hence no oracle/_ref.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+P = 0xFFFFFFFF00000001
+
+E_LEN_NOT_POW2 = -1
+E_LEN_TOO_LARGE = -2
+E_TOO_FEW_LEAFS = -3
+E_INCORRECT_NUMBER_OF_LEAFS = -4
+E_ORDER_LE_DEGREE = -5
+
+
+def build(native: bool = False, force: bool = False) -> str:
+    """Compile oracle.c with gcc. native=True uses -march=native (for CPU-baseline timing on
+    the box the benchmark runs on) and writes a separate file."""
+    out = os.path.join(_BUILD, "liboracle_native.so" if native else "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "field.h")]
+    if not force and os.path.exists(out) and all(
+        os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs
+    ):
+        return out
+    os.makedirs(_BUILD, exist_ok=True)
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    march = "native" if native else "x86-64-v3"
+    cmd = [cc, "-O3", f"-march={march}", "-fopenmp", "-fPIC", "-std=gnu11", "-shared",
+           "-o", out, os.path.join(_HERE, "oracle.c")]
+    subprocess.run(cmd, check=True, cwd=_HERE)
+    return out
+
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def _ptr(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_u64p)
+
+
+class Oracle:
+    def __init__(self, native: bool = False):
+        path = build(native=native)
+        try:
+            self.lib = ctypes.CDLL(path)
+        except OSError:
+            path = build(native=native, force=True)
+            self.lib = ctypes.CDLL(path)
+        L = self.lib
+        u64, u32, i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+        L.oracle_ntt.argtypes = [_u64p, u64, u32]
+        L.oracle_intt.argtypes = [_u64p, u64, u32]
+        L.oracle_ntt_batch.argtypes = [_u64p, u64, u32, u64, i32, i32]
+        L.oracle_poly_scale.argtypes = [_u64p, u64, u32, u64]
+        L.oracle_poly_scale.restype = None
+        L.oracle_coset_evaluate.argtypes = [_u64p, u64, u32, u64, u64, _u64p]
+        L.oracle_coset_interpolate.argtypes = [_u64p, u64, u32, u64, _u64p]
+        L.oracle_poly_evaluate.argtypes = [_u64p, u64, u64]
+        L.oracle_poly_evaluate.restype = u64
+        L.oracle_tip5_permutation.argtypes = [_u64p]
+        L.oracle_tip5_permutation.restype = None
+        L.oracle_tip5_hash_10.argtypes = [_u64p, _u64p]
+        L.oracle_tip5_hash_10.restype = None
+        L.oracle_tip5_hash_pair.argtypes = [_u64p, _u64p, _u64p]
+        L.oracle_tip5_hash_pair.restype = None
+        L.oracle_tip5_hash_varlen.argtypes = [_u64p, u64, _u64p]
+        L.oracle_tip5_hash_varlen.restype = None
+        L.oracle_tip5_hasher_bytes.argtypes = [_u8p, u64]
+        L.oracle_tip5_hasher_bytes.restype = u64
+        L.oracle_tip5_permute_batch.argtypes = [_u64p, u64, i32]
+        L.oracle_tip5_permute_batch.restype = None
+        L.oracle_tip5_hash_pairs_batch.argtypes = [_u64p, u64, _u64p, i32]
+        L.oracle_tip5_hash_pairs_batch.restype = None
+        L.oracle_digest_to_hex.argtypes = [_u64p, ctypes.c_char_p]
+        L.oracle_digest_to_hex.restype = None
+        L.oracle_merkle_sequential_new.argtypes = [_u64p, u64, _u64p]
+        L.oracle_merkle_par_new.argtypes = [_u64p, u64, _u64p, i32, u64]
+        L.oracle_merkle_sequential_frugal_root.argtypes = [_u64p, u64, _u64p]
+        L.oracle_merkle_par_frugal_root.argtypes = [_u64p, u64, _u64p, i32, u64]
+        for name in ("new", "value", "inverse_or_zero", "primitive_root_of_unity"):
+            f = getattr(L, f"oracle_bfe_{name}")
+            f.argtypes = [u64]
+            f.restype = u64
+        for name in ("add", "sub", "mul", "mod_pow"):
+            f = getattr(L, f"oracle_bfe_{name}")
+            f.argtypes = [u64, u64]
+            f.restype = u64
+        L.oracle_bfe_new_array.argtypes = [_u64p, u64]
+        L.oracle_bfe_new_array.restype = None
+        L.oracle_bfe_value_array.argtypes = [_u64p, u64]
+        L.oracle_bfe_value_array.restype = None
+        L.oracle_num_threads.restype = i32
+
+    # ---- field ---------------------------------------------------------------------------
+    def bfe_new(self, v: int) -> int:
+        return self.lib.oracle_bfe_new(v % (1 << 64))
+
+    def bfe_value(self, raw: int) -> int:
+        return self.lib.oracle_bfe_value(raw)
+
+    def bfe_add(self, a, b):
+        return self.lib.oracle_bfe_add(a, b)
+
+    def bfe_sub(self, a, b):
+        return self.lib.oracle_bfe_sub(a, b)
+
+    def bfe_mul(self, a, b):
+        return self.lib.oracle_bfe_mul(a, b)
+
+    def bfe_mod_pow(self, a, e):
+        return self.lib.oracle_bfe_mod_pow(a, e)
+
+    def bfe_inverse_or_zero(self, a):
+        return self.lib.oracle_bfe_inverse_or_zero(a)
+
+    def primitive_root_of_unity(self, n: int) -> int:
+        return self.lib.oracle_bfe_primitive_root_of_unity(n)
+
+    def to_raw(self, values) -> np.ndarray:
+        """canonical values -> raw Montgomery words (BFieldElement::new element-wise)"""
+        a = np.ascontiguousarray(np.array(values, dtype=np.uint64).copy())
+        self.lib.oracle_bfe_new_array(_ptr(a.reshape(-1)), a.size)
+        return a
+
+    def to_values(self, raw) -> np.ndarray:
+        a = np.ascontiguousarray(np.array(raw, dtype=np.uint64).copy())
+        self.lib.oracle_bfe_value_array(_ptr(a.reshape(-1)), a.size)
+        return a
+
+    # ---- ntt -----------------------------------------------------------------------------
+    def ntt(self, x: np.ndarray, width: int = 1) -> int:
+        """in place; x has n*width words"""
+        return self.lib.oracle_ntt(_ptr(x), x.size // width, width)
+
+    def intt(self, x: np.ndarray, width: int = 1) -> int:
+        return self.lib.oracle_intt(_ptr(x), x.size // width, width)
+
+    def ntt_batch(self, x: np.ndarray, n: int, width: int, batch: int, inverse: bool,
+                  threads: int = 0) -> int:
+        assert x.size == n * width * batch
+        return self.lib.oracle_ntt_batch(_ptr(x), n, width, batch, int(inverse), threads)
+
+    # ---- polynomial ------------------------------------------------------------------------
+    def poly_scale(self, coeffs: np.ndarray, width: int, alpha_raw: int) -> None:
+        self.lib.oracle_poly_scale(_ptr(coeffs), coeffs.size // width, width, alpha_raw)
+
+    def coset_evaluate(self, coeffs: np.ndarray, width: int, offset_raw: int, order: int):
+        out = np.zeros(order * width, dtype=np.uint64)
+        rc = self.lib.oracle_coset_evaluate(_ptr(coeffs), coeffs.size // width, width,
+                                            offset_raw, order, _ptr(out))
+        return rc, out
+
+    def coset_interpolate(self, values: np.ndarray, width: int, offset_raw: int):
+        out = np.zeros(values.size, dtype=np.uint64)
+        rc = self.lib.oracle_coset_interpolate(_ptr(values), values.size // width, width,
+                                               offset_raw, _ptr(out))
+        return rc, out
+
+    def poly_evaluate(self, coeffs: np.ndarray, x_raw: int) -> int:
+        return self.lib.oracle_poly_evaluate(_ptr(coeffs), coeffs.size, x_raw)
+
+    # ---- tip5 ------------------------------------------------------------------------------
+    def tip5_permutation(self, state: np.ndarray) -> None:
+        assert state.size == 16
+        self.lib.oracle_tip5_permutation(_ptr(state))
+
+    def tip5_permute_batch(self, states: np.ndarray, threads: int = 0) -> None:
+        self.lib.oracle_tip5_permute_batch(_ptr(states), states.size // 16, threads)
+
+    def hash_10(self, inp: np.ndarray) -> np.ndarray:
+        out = np.zeros(5, dtype=np.uint64)
+        self.lib.oracle_tip5_hash_10(_ptr(inp), _ptr(out))
+        return out
+
+    def hash_pair(self, left: np.ndarray, right: np.ndarray) -> np.ndarray:
+        out = np.zeros(5, dtype=np.uint64)
+        self.lib.oracle_tip5_hash_pair(_ptr(left), _ptr(right), _ptr(out))
+        return out
+
+    def hash_pairs_batch(self, pairs: np.ndarray, threads: int = 0) -> np.ndarray:
+        count = pairs.size // 10
+        out = np.zeros(5 * count, dtype=np.uint64)
+        self.lib.oracle_tip5_hash_pairs_batch(_ptr(pairs), count, _ptr(out), threads)
+        return out
+
+    def hash_varlen(self, inp: np.ndarray) -> np.ndarray:
+        out = np.zeros(5, dtype=np.uint64)
+        inp = np.ascontiguousarray(inp, dtype=np.uint64)
+        buf = inp if inp.size else np.zeros(1, dtype=np.uint64)
+        self.lib.oracle_tip5_hash_varlen(_ptr(buf), inp.size, _ptr(out))
+        return out
+
+    def hasher_bytes(self, data: bytes) -> int:
+        buf = (ctypes.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+        return self.lib.oracle_tip5_hasher_bytes(buf, len(data))
+
+    def digest_to_hex(self, digest_raw: np.ndarray) -> str:
+        out = ctypes.create_string_buffer(81)
+        self.lib.oracle_digest_to_hex(_ptr(np.ascontiguousarray(digest_raw, dtype=np.uint64)), out)
+        return out.value.decode()
+
+    # ---- merkle ----------------------------------------------------------------------------
+    def merkle_sequential_new(self, leafs: np.ndarray):
+        n = leafs.size // 5
+        nodes = np.zeros(max(1, 10 * n), dtype=np.uint64)
+        rc = self.lib.oracle_merkle_sequential_new(_ptr(leafs if n else nodes), n, _ptr(nodes))
+        return rc, nodes[: 10 * n]
+
+    def merkle_par_new(self, leafs: np.ndarray, threads: int = 0, cutoff: int = 512):
+        n = leafs.size // 5
+        nodes = np.zeros(max(1, 10 * n), dtype=np.uint64)
+        rc = self.lib.oracle_merkle_par_new(_ptr(leafs if n else nodes), n, _ptr(nodes), threads, cutoff)
+        return rc, nodes[: 10 * n]
+
+    def merkle_sequential_frugal_root(self, leafs: np.ndarray):
+        n = leafs.size // 5
+        root = np.zeros(5, dtype=np.uint64)
+        rc = self.lib.oracle_merkle_sequential_frugal_root(_ptr(leafs if n else root), n, _ptr(root))
+        return rc, root
+
+    def merkle_par_frugal_root(self, leafs: np.ndarray, threads: int = 0, cutoff: int = 512):
+        n = leafs.size // 5
+        root = np.zeros(5, dtype=np.uint64)
+        rc = self.lib.oracle_merkle_par_frugal_root(_ptr(leafs if n else root), n, _ptr(root), threads, cutoff)
+        return rc, root
+
+    def num_threads(self) -> int:
+        return self.lib.oracle_num_threads()
+
+
+_default = None
+
+
+def get(native: bool = False) -> Oracle:
+    global _default
+    if native:
+        return Oracle(native=True)
+    if _default is None:
+        _default = Oracle()
+    return _default
+
+
+def splitmix64_words(seed: int, count: int) -> np.ndarray:
+    """SURVEY.md 8(d) synthetic-input generator: SplitMix64 stream, values >= p rejected, used
+    directly as raw words (x R is a bijection on F_p).  Vectorised: draws with a small surplus and
+    filters (deterministic for a given seed and count)."""
+    out = np.empty(count, dtype=np.uint64)
+    filled = 0
+    state = np.uint64(seed)
+    GAMMA = np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        while filled < count:
+            m = max(1024, int((count - filled) * 1.001) + 16)
+            idx = np.arange(1, m + 1, dtype=np.uint64)
+            z = state + idx * GAMMA
+            state = z[-1]
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            z = z[z < np.uint64(P)]
+            take = min(z.size, count - filled)
+            out[filled:filled + take] = z[:take]
+            filled += take
+    return out
