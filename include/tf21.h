@@ -1,0 +1,130 @@
+/*
+ * tf21.h -- C ABI of the B200-native (sm_100a) replacement for twenty-first's STARK hot path.
+ *
+ * This is the drop-in boundary: a Rust shim keeps the reference's public signatures
+ * (`math::ntt::{ntt,intt}`, `Polynomial::fast_coset_{evaluate,interpolate}`, `Tip5::*`,
+ * `MerkleTree::{par_new,sequential_new,par_frugal_root,sequential_frugal_root}`) and calls the
+ * entry points below (see INTEGRATION.md for the binding).  Reference paths are relative to
+ * twenty-first/src/ of Neptune-Crypto/twenty-first v2.0.2.
+ *
+ * Conventions
+ *  - Every word is the raw in-memory u64 of a `BFieldElement` (Montgomery form, canonical,
+ *    b_field_element.rs:84-86).  `width` = 1 for `[BFieldElement]`, 3 for `[XFieldElement]`
+ *    (`#[repr(transparent)] [BFieldElement; 3]`, x_field_element.rs:56-59).  A Digest is 5 words
+ *    (tip5/digest.rs:28-29).
+ *  - Return value: 0 on success, a negative TF21_E_* code otherwise.  Nothing aborts or throws
+ *    across the boundary; the shim turns codes back into the reference's behaviour (panic for
+ *    NTT length violations, Err(MerkleTreeError::..) for Merkle).
+ *  - The caller owns every buffer; the library keeps no pointer past return.
+ *  - Host-pointer entry points copy host->device->host internally on the calling thread's
+ *    current CUDA device.  `*_dev` entry points take device pointers plus a stream
+ *    (cudaStream_t passed as void*; NULL = default stream) and are asynchronous.
+ *  - Thread safe: tables are built once per (device, size) under a lock; scratch is per call
+ *    or per (device, stream) cache guarded by a lock.
+ *  - There is no CPU fallback: without a usable CUDA device every call returns TF21_E_CUDA.
+ */
+#ifndef TF21_H
+#define TF21_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    TF21_OK = 0,
+    TF21_E_LEN_NOT_POW2 = -1,    /* ntt.rs:137 `assert!(len == 0 || is_power_of_two)` (panic)        */
+    TF21_E_LEN_TOO_LARGE = -2,   /* ntt.rs:135-136 len > u32::MAX (panic); also the 2^30 device limit */
+    TF21_E_TOO_FEW_LEAFS = -3,   /* MerkleTreeError::TooFewLeafs, merkle_tree.rs:394-396            */
+    TF21_E_INCORRECT_NUMBER_OF_LEAFS = -4, /* MerkleTreeError::IncorrectNumberOfLeafs, :398-401     */
+    TF21_E_ORDER_LE_DEGREE = -5, /* polynomial.rs:1388-1392 assert (panic)                           */
+    TF21_E_ALLOC = -6,           /* MerkleTreeError::TreeTooHigh, merkle_tree.rs:403-410 / cudaMalloc */
+    TF21_E_CUDA = -7,            /* any CUDA runtime failure; see tf21_last_cuda_error()             */
+    TF21_E_BAD_ARG = -8,         /* width not in {1,3}, NULL pointer with non-zero size, ...         */
+};
+
+typedef void *tf21_stream_t; /* cudaStream_t */
+
+/* ---- runtime -------------------------------------------------------------------------------- */
+/* Selects `device` for the calling thread (cudaSetDevice) and uploads the constant tables.      */
+int tf21_init(int device);
+/* Frees cached tables and scratch of every device touched by this process.                     */
+int tf21_shutdown(void);
+const char *tf21_strerror(int code);
+const char *tf21_last_cuda_error(void);
+/* Number of kernels launched by this library in this process since start (bench bookkeeping).  */
+uint64_t tf21_kernel_launch_count(void);
+/* Stream-ordered device memory helpers so a host language needs no CUDA binding of its own.   */
+int tf21_malloc(void **dptr, uint64_t bytes);
+int tf21_free(void *dptr);
+int tf21_memcpy_h2d(void *dst_dev, const void *src_host, uint64_t bytes, tf21_stream_t stream);
+int tf21_memcpy_d2h(void *dst_host, const void *src_dev, uint64_t bytes, tf21_stream_t stream);
+int tf21_stream_sync(tf21_stream_t stream);
+
+/* ---- NTT: math::ntt::ntt / intt (ntt.rs:67-82, 109-125) ------------------------------------- */
+/* In place over `batch` contiguous arrays of n*width words. n == 0 or 1 is a no-op.
+ * out[i] = sum_j x[j] * omega_n^(i j), natural order in and out; intt also multiplies by n^-1.  */
+int tf21_ntt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch);
+int tf21_intt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch);
+int tf21_ntt_dev(uint64_t *d_data, uint64_t n, uint32_t width, uint64_t batch, int inverse,
+                 tf21_stream_t stream);
+
+/* ---- coset evaluate / interpolate: math::polynomial (polynomial.rs:760-773,1374-1399,1907-1918) */
+/* out[0..order*width) = NTT_order( zero_extend( c[i] * offset^i ) ); requires order > degree.    */
+int tf21_coset_evaluate(const uint64_t *coeffs, uint64_t n_coeffs, uint32_t width,
+                        uint64_t offset_raw, uint64_t order, uint64_t *out);
+/* coeffs_out[i] = iNTT_n(values)[i] * offset^-i ; all n coefficients are returned.               */
+int tf21_coset_interpolate(const uint64_t *values, uint64_t n, uint32_t width, uint64_t offset_raw,
+                           uint64_t *coeffs_out);
+/* Fused low-degree extension = interpolate on (offset_in, n_in) then evaluate on
+ * (offset_out, n_out), n_out >= n_in.                                                           */
+int tf21_coset_lde(const uint64_t *values, uint64_t n_in, uint64_t offset_in_raw, uint64_t n_out,
+                   uint64_t offset_out_raw, uint32_t width, uint64_t *out);
+/* Device variants. `d_out` must not alias the input. The degree check of evaluate is skipped on
+ * device (the caller guarantees n_coeffs <= order); n_coeffs > order returns ORDER_LE_DEGREE.   */
+int tf21_coset_evaluate_dev(const uint64_t *d_coeffs, uint64_t n_coeffs, uint32_t width,
+                            uint64_t offset_raw, uint64_t order, uint64_t *d_out,
+                            tf21_stream_t stream);
+int tf21_coset_interpolate_dev(const uint64_t *d_values, uint64_t n, uint32_t width,
+                               uint64_t offset_raw, uint64_t *d_coeffs_out, tf21_stream_t stream);
+int tf21_coset_lde_dev(const uint64_t *d_values, uint64_t n_in, uint64_t offset_in_raw,
+                       uint64_t n_out, uint64_t offset_out_raw, uint32_t width, uint64_t *d_out,
+                       tf21_stream_t stream);
+
+/* ---- Tip5 (tip5/mod.rs:529-533, 559-586, 617-623; sponge.rs:41-56) -------------------------- */
+int tf21_tip5_permute(uint64_t *states /*16 words each*/, uint64_t count);
+int tf21_tip5_hash_10(const uint64_t *in /*10 words each*/, uint64_t count, uint64_t *out /*5 each*/);
+int tf21_tip5_hash_pairs(const uint64_t *pairs /*left(5)|right(5)*/, uint64_t count, uint64_t *out);
+/* hash_varlen of one sequence (sequential sponge; runs on the device, latency bound).          */
+int tf21_tip5_hash_varlen(const uint64_t *in, uint64_t len, uint64_t out[5]);
+/* hash_varlen of `n_rows` rows of `row_len` words each (row-major) -> n_rows digests: the step
+ * that turns NTT codewords into Merkle leaves in the crate's callers.                          */
+int tf21_tip5_hash_rows(const uint64_t *rows, uint64_t row_len, uint64_t n_rows, uint64_t *out);
+int tf21_tip5_permute_dev(uint64_t *d_states, uint64_t count, tf21_stream_t stream);
+int tf21_tip5_hash_10_dev(const uint64_t *d_in, uint64_t count, uint64_t *d_out, tf21_stream_t stream);
+int tf21_tip5_hash_rows_dev(const uint64_t *d_rows, uint64_t row_len, uint64_t n_rows,
+                            uint64_t *d_out, tf21_stream_t stream);
+
+/* ---- Merkle tree (merkle_tree.rs:149-222, 299-364, 393-429) -------------------------------- */
+/* nodes_out has 2*n_leafs digests: nodes[0] = 0, nodes[1] = root,
+ * nodes[i] = hash_pair(nodes[2i], nodes[2i+1]), nodes[n..2n) = leafs.                          */
+int tf21_merkle_build(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out);
+int tf21_merkle_root(const uint64_t *leafs, uint64_t n_leafs, uint64_t root_out[5]);
+int tf21_merkle_build_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d_nodes_out,
+                          tf21_stream_t stream);
+int tf21_merkle_root_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d_root_out,
+                         tf21_stream_t stream);
+/* Multi-GPU assembly (subtrees shard independently, merkle_tree.rs:247-275): rank `shard` of
+ * `n_shards` builds its local tree with tf21_merkle_build_dev over its n_leafs/n_shards leaves;
+ * after the cap (the n_shards local roots) has been gathered, the top of the tree is
+ * tf21_merkle_build_dev over those roots.  This scatters a local tree into its positions in the
+ * global heap-indexed node array (only needed when one device wants the whole array).          */
+int tf21_merkle_scatter_subtree_dev(const uint64_t *d_local_nodes, uint64_t n_local_leafs,
+                                    uint64_t shard, uint64_t n_shards, uint64_t *d_global_nodes,
+                                    tf21_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TF21_H */

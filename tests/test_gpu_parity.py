@@ -1,0 +1,326 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libtf21.so), against the CPU
+oracle on identical seeded inputs, against the reference's golden vectors, and -- at full
+BASELINE.json sizes -- through size-independent properties.  Bit-exact everywhere (integer work)."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+P = 0xFFFFFFFF00000001
+
+
+@pytest.fixture(scope="module")
+def tf():
+    mod = importlib.import_module("twenty-first_b200")
+    mod.check(mod.lib.tf21_init(0))
+    return mod
+
+
+def _h(xs):
+    return [int(x, 16) if isinstance(x, str) else int(x) for x in xs]
+
+
+def rnd(seed, count):
+    import oracle as o
+
+    return o.splitmix64_words(seed, count)
+
+
+def adversarial(n, w=1):
+    """all-zero, all p-1, unit impulses, lanes 0xffffffff00000000"""
+    total = n * w
+    sets = [np.zeros(total, dtype=np.uint64), np.full(total, P - 1, dtype=np.uint64),
+            np.full(total, 0xFFFFFFFF00000000, dtype=np.uint64)]
+    for pos in {0, total - 1, total // 2}:
+        e = np.zeros(total, dtype=np.uint64)
+        e[pos] = 0xFFFFFFFF  # raw one
+        sets.append(e)
+    return sets
+
+
+# ---- NTT --------------------------------------------------------------------------------------------
+def test_ntt_reference_kats(tf, oracle, kats):
+    for name in ("bfield_basic", "bfield_max", "bfield_len32"):
+        k = kats["ntt"][name]
+        x = oracle.to_raw(k["input_values"])
+        orig = x.copy()
+        tf.ntt(x)
+        assert [int(v) for v in oracle.to_values(x)] == k["expected_values"], name
+        tf.intt(x)
+        assert np.array_equal(x, orig)
+    k = kats["ntt"]["xfield_basic"]
+    x = oracle.to_raw(np.array(k["input_values"], dtype=np.uint64))
+    orig = x.copy()
+    tf.ntt(x)
+    assert oracle.to_values(x).tolist() == k["expected_values"]
+    tf.intt(x)
+    assert np.array_equal(x, orig)
+
+
+@pytest.mark.parametrize("log2n", list(range(0, 15)) + [16, 18, 20, 21])
+def test_bfe_ntt_matches_oracle(tf, oracle, log2n):
+    n = 1 << log2n
+    inputs = [rnd(100 + log2n, n)] + (adversarial(n) if log2n <= 12 or log2n == 20 else [])
+    for x in inputs:
+        want = x.copy()
+        assert oracle.ntt(want, 1) == 0
+        got = x.copy()
+        tf.ntt(got)
+        assert np.array_equal(got, want)
+        assert (got < np.uint64(P)).all()
+        want_i = x.copy()
+        oracle.intt(want_i, 1)
+        got_i = x.copy()
+        tf.intt(got_i)
+        assert np.array_equal(got_i, want_i)
+        tf.intt(got)
+        assert np.array_equal(got, x)
+
+
+@pytest.mark.parametrize("log2n", list(range(0, 13)) + [15, 20, 22])
+def test_xfe_ntt_matches_oracle(tf, oracle, log2n):
+    n = 1 << log2n
+    inputs = [rnd(200 + log2n, 3 * n)] + (adversarial(n, 3) if log2n <= 10 else [])
+    for flat in inputs:
+        want = flat.copy()
+        oracle.ntt(want, 3)
+        got = flat.copy().reshape(n, 3)
+        tf.ntt(got)
+        assert np.array_equal(got.reshape(-1), want)
+        want_i = flat.copy()
+        oracle.intt(want_i, 3)
+        got_i = flat.copy().reshape(n, 3)
+        tf.intt(got_i)
+        assert np.array_equal(got_i.reshape(-1), want_i)
+
+
+def test_ntt_edge_cases_and_errors(tf):
+    # ntt.rs:471-498 (empty, length one, 0-1-0) and the panics of ntt.rs:135-137
+    api = importlib.import_module("twenty-first_b200.api")
+    e = np.zeros(0, dtype=np.uint64)
+    tf.ntt(e)
+    tf.intt(e)
+    one = np.array([12345], dtype=np.uint64)
+    tf.ntt(one)
+    assert int(one[0]) == 12345
+    tf.ntt(e)
+    for bad in (3, 12, 1000):
+        with pytest.raises(tf.Tf21Error) as ei:
+            tf.ntt(np.zeros(bad, dtype=np.uint64))
+        assert ei.value.code == tf.E_LEN_NOT_POW2
+    assert tf.lib.tf21_ntt(None, 1 << 33, 1, 1) == tf.E_LEN_TOO_LARGE
+    assert tf.lib.tf21_ntt(None, 8, 2, 1) == tf.E_BAD_ARG
+    assert api is not None
+
+
+@pytest.mark.parametrize("log2n,width,batch", [(3, 1, 5), (10, 1, 33), (10, 3, 7), (12, 1, 9), (16, 1, 4), (20, 1, 3), (11, 3, 5)])
+def test_batched_ntt_matches_oracle(tf, oracle, log2n, width, batch):
+    api = importlib.import_module("twenty-first_b200.api")
+    n = 1 << log2n
+    x = rnd(300 + log2n + batch, n * width * batch)
+    for inverse in (False, True):
+        want = x.copy()
+        assert oracle.ntt_batch(want, n, width, batch, inverse) == 0
+        got = x.copy()
+        api.ntt_batch(got, n, width, inverse)
+        assert np.array_equal(got, want)
+
+
+def test_ntt_linearity_and_impulse_at_2_20(tf, oracle):
+    n = 1 << 20
+    a, b = rnd(1, n), rnd(2, n)
+    s = np.array([oracle.bfe_add(int(x), int(y)) for x, y in zip(a[:64], b[:64])], dtype=np.uint64)
+    fa, fb = a.copy(), b.copy()
+    tf.ntt(fa)
+    tf.ntt(fb)
+    # NTT(a)+NTT(b) == NTT(a+b) checked on a sparse vector to keep the CPU side cheap
+    sp_a = np.zeros(n, dtype=np.uint64)
+    sp_b = np.zeros(n, dtype=np.uint64)
+    sp_a[:64] = a[:64]
+    sp_b[:64] = b[:64]
+    sp_s = np.zeros(n, dtype=np.uint64)
+    sp_s[:64] = s
+    tf.ntt(sp_a)
+    tf.ntt(sp_b)
+    tf.ntt(sp_s)
+    idx = np.arange(0, n, 4099)
+    for i in idx:
+        assert int(sp_s[i]) == oracle.bfe_add(int(sp_a[i]), int(sp_b[i]))
+    # impulse at position 1 -> powers of omega (raw-one times omega^i)
+    imp = np.zeros(n, dtype=np.uint64)
+    imp[1] = 0xFFFFFFFF
+    tf.ntt(imp)
+    omega = oracle.primitive_root_of_unity(n)
+    for i in (0, 1, 2, 12345, n - 1):
+        assert int(imp[i]) == oracle.bfe_mod_pow(omega, i)
+
+
+# ---- coset ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log_coeffs,log_order,width", [(0, 0, 1), (0, 3, 1), (3, 3, 1), (5, 9, 1), (10, 10, 3), (8, 12, 3), (12, 16, 1), (14, 21, 1), (13, 17, 3)])
+def test_coset_evaluate_interpolate_match_oracle(tf, oracle, log_coeffs, log_order, width):
+    nc, order = 1 << log_coeffs, 1 << log_order
+    coeffs = rnd(400 + log_coeffs * 31 + log_order, nc * width)
+    offset = int(rnd(77 + log_order, 1)[0])
+    rc, want = oracle.coset_evaluate(coeffs, width, offset, order)
+    assert rc == 0
+    poly = tf.Polynomial(coeffs.reshape(nc, 3) if width == 3 else coeffs)
+    got = poly.fast_coset_evaluate(offset, order)
+    assert np.array_equal(got.reshape(-1), want)
+    rc, want_c = oracle.coset_interpolate(want, width, offset)
+    got_c = tf.Polynomial.fast_coset_interpolate(offset, got).coefficients
+    assert np.array_equal(got_c.reshape(-1), want_c)
+    assert np.array_equal(got_c.reshape(-1)[: nc * width], coeffs)
+    assert not got_c.reshape(-1)[nc * width:].any()
+
+
+def test_coset_evaluate_degree_rules(tf, oracle):
+    coeffs = rnd(3, 8)
+    g = tf.BFieldElement.generator()
+    with pytest.raises(tf.Tf21Error) as ei:
+        tf.Polynomial(coeffs).fast_coset_evaluate(g, 4)
+    assert ei.value.code == tf.E_ORDER_LE_DEGREE
+    coeffs[4:] = 0  # trailing zeros do not count (Polynomial::new strips them)
+    got = tf.Polynomial(coeffs).fast_coset_evaluate(g, 4)
+    rc, want = oracle.coset_evaluate(coeffs, 1, g, 4)
+    assert rc == 0 and np.array_equal(got, want)
+    # the zero polynomial evaluates to zeros on any domain, including order 0
+    z = tf.Polynomial(np.zeros(4, dtype=np.uint64)).fast_coset_evaluate(g, 8)
+    assert not z.any()
+
+
+@pytest.mark.parametrize("log_in,log_out,width", [(0, 0, 1), (0, 4, 3), (4, 4, 1), (6, 10, 3), (10, 14, 1), (12, 16, 3), (16, 20, 3)])
+def test_coset_lde_matches_oracle(tf, oracle, log_in, log_out, width):
+    n_in, n_out = 1 << log_in, 1 << log_out
+    values = rnd(500 + log_in + log_out, n_in * width)
+    g = tf.BFieldElement.generator()
+    g_in, g_out = g, (g if log_in % 2 == 0 else tf.BFieldElement.new(49))
+    rc, coeffs = oracle.coset_interpolate(values, width, g_in)
+    assert rc == 0
+    rc, want = oracle.coset_evaluate(coeffs, width, g_out, n_out)
+    assert rc == 0
+    got = tf.Polynomial.coset_lde(values.reshape(n_in, 3) if width == 3 else values, g_in, n_out, g_out)
+    assert np.array_equal(got.reshape(-1), want)
+
+
+# ---- Tip5 --------------------------------------------------------------------------------------------
+def test_tip5_reference_kats(tf, oracle, kats):
+    t = kats["tip5"]
+    pre = np.zeros(10, dtype=np.uint64)
+    for i in range(6):
+        pre[i:i + 5] = tf.Tip5.hash_10(pre)
+    assert tf.Digest.to_hex(tf.Tip5.hash_10(pre)) == t["hash10_snapshot"]["hex"]
+
+    acc = np.zeros(5, dtype=np.uint64)
+    for i in range(20):
+        d = tf.Tip5.hash_varlen(oracle.to_raw(list(range(i))) if i else np.zeros(0, dtype=np.uint64))
+        acc = np.array([oracle.bfe_add(int(a), int(b)) for a, b in zip(acc, d)], dtype=np.uint64)
+    assert tf.Digest.to_hex(acc) == t["hash_varlen_sum"]["hex"]
+
+    s = np.array(_h(t["raw_snapshot"]["state_raw"]), dtype=np.uint64)
+    tf.Tip5.permutation(s)
+    assert [int(v) for v in s[:5]] == _h(t["raw_snapshot"]["expected_first5_raw"])
+
+    s = oracle.to_raw(_h(t["degenerate"]["state_values"]))
+    tf.Tip5.permutation(s)
+    assert [int(v) for v in oracle.to_values(s)] == _h(t["degenerate"]["expected_values"])
+
+
+def test_tip5_batches_match_oracle(tf, oracle):
+    for count in (1, 2, 31, 128, 129, 5000):
+        states = rnd(600 + count, 16 * count)
+        want = states.copy()
+        oracle.tip5_permute_batch(want)
+        got = states.copy().reshape(count, 16)
+        tf.Tip5.permutation(got)
+        assert np.array_equal(got.reshape(-1), want)
+        pairs = rnd(700 + count, 10 * count)
+        want_h = oracle.hash_pairs_batch(pairs)
+        got_h = tf.Tip5.hash_10(pairs.reshape(count, 10))
+        assert np.array_equal(got_h.reshape(-1), want_h)
+        got_p = tf.Tip5.hash_pair(np.ascontiguousarray(pairs.reshape(count, 10)[:, :5]),
+                                  np.ascontiguousarray(pairs.reshape(count, 10)[:, 5:]))
+        assert np.array_equal(got_p.reshape(-1), want_h)
+    # adversarial lanes
+    for fill in (0, P - 1, 0xFFFFFFFF00000000, 0xFFFFFFFF):
+        st = np.full(16 * 3, fill, dtype=np.uint64)
+        want = st.copy()
+        oracle.tip5_permute_batch(want)
+        got = st.copy()
+        tf.Tip5.permutation(got)
+        assert np.array_equal(got, want)
+
+
+def test_tip5_hash_varlen_and_rows_match_oracle(tf, oracle):
+    for length in (0, 1, 9, 10, 11, 19, 20, 21, 100, 16384):
+        x = rnd(800 + length, length)
+        assert np.array_equal(tf.Tip5.hash_varlen(x), oracle.hash_varlen(x)), length
+    for row_len, n_rows in ((1, 7), (10, 130), (33, 257), (0, 3)):
+        rows = rnd(900 + row_len, row_len * n_rows).reshape(n_rows, row_len)
+        got = tf.Tip5.hash_rows(rows)
+        for r in range(0, n_rows, max(1, n_rows // 9)):
+            assert np.array_equal(got[r], oracle.hash_varlen(np.ascontiguousarray(rows[r])))
+
+
+# ---- Merkle -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("height", list(range(0, 15)) + [17, 20])
+def test_merkle_tree_matches_oracle(tf, oracle, height):
+    n = 1 << height
+    leafs = rnd(0x5000 + height, 5 * n)
+    rc, want = oracle.merkle_par_new(leafs)
+    assert rc == 0
+    tree = tf.MerkleTree.par_new(leafs.reshape(n, 5))
+    assert np.array_equal(tree.nodes.reshape(-1), want)
+    assert not tree.nodes[0].any()
+    assert tree.num_leafs() == n and tree.height() == height
+    assert np.array_equal(tree.leafs().reshape(-1), leafs)
+    assert np.array_equal(tf.MerkleTree.par_frugal_root(leafs.reshape(n, 5)), want[5:10])
+    assert np.array_equal(tf.MerkleTree.sequential_frugal_root(leafs.reshape(n, 5)), tree.root())
+
+
+def test_merkle_errors(tf):
+    # merkle_tree.rs:1025-1057
+    e = np.zeros((0, 5), dtype=np.uint64)
+    with pytest.raises(tf.MerkleTreeError) as ei:
+        tf.MerkleTree.par_new(e)
+    assert ei.value.kind == "TooFewLeafs"
+    with pytest.raises(tf.MerkleTreeError) as ei:
+        tf.MerkleTree.sequential_frugal_root(e)
+    assert ei.value.kind == "TooFewLeafs"
+    with pytest.raises(tf.MerkleTreeError) as ei:
+        tf.MerkleTree.par_frugal_root(e)
+    assert ei.value.kind == "IncorrectNumberOfLeafs"
+    for n in (3, 5, 6, 7, 12, 1023):
+        with pytest.raises(tf.MerkleTreeError) as ei:
+            tf.MerkleTree.par_new(np.zeros((n, 5), dtype=np.uint64))
+        assert ei.value.kind == "IncorrectNumberOfLeafs"
+        with pytest.raises(tf.MerkleTreeError):
+            tf.MerkleTree.par_frugal_root(np.zeros((n, 5), dtype=np.uint64))
+
+
+def test_merkle_sharded_assembly_equals_single_tree(tf, oracle):
+    """(e) of SURVEY.md: subtrees built independently + cap == one tree; scatter reproduces nodes."""
+    import torch
+
+    dev = importlib.import_module("twenty-first_b200.device")
+    height, shards = 12, 4
+    n = 1 << height
+    leafs = rnd(0x7777, 5 * n)
+    rc, want = oracle.merkle_par_new(leafs)
+    cuda = torch.device("cuda:0")
+    nl = n // shards
+    global_nodes = torch.zeros(10 * n, dtype=torch.int64, device=cuda)
+    roots = torch.zeros(5 * shards, dtype=torch.int64, device=cuda)
+    for g in range(shards):
+        shard = torch.from_numpy(leafs[5 * g * nl: 5 * (g + 1) * nl].view(np.int64)).to(cuda)
+        local = torch.zeros(10 * nl, dtype=torch.int64, device=cuda)
+        dev.merkle_build(shard, local)
+        roots[5 * g: 5 * g + 5] = local[5:10]
+        dev.merkle_scatter_subtree(local, g, shards, global_nodes)
+    cap = torch.zeros(10 * shards, dtype=torch.int64, device=cuda)
+    dev.merkle_build(roots, cap)
+    global_nodes[: 5 * shards] = cap[: 5 * shards]
+    torch.cuda.synchronize()
+    got = global_nodes.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)

@@ -1,0 +1,162 @@
+// field.cuh -- Goldilocks (p = 2^64 - 2^32 + 1) arithmetic for sm_100a.
+//
+// Replaces the scalar Montgomery arithmetic of the reference
+// (twenty-first/src/math/b_field_element.rs:357-370 montyred, :711-732 Add, :773-795 Sub, :755-762 Mul).
+// The kernels never use Montgomery multiplication: NTT is F_p-linear and Tip5's S-box exponent 7
+// satisfies R^6 = 1, so plain mod-p arithmetic on the raw Montgomery words with canonical
+// twiddles / raw round constants reproduces the reference bit for bit.
+//
+// Representation inside kernels: "weak" = any u64 (value mod p, possibly >= p).  Only the final
+// store (and Tip5's LUT lanes) canonicalise to [0, p).
+//
+// Instruction budget (SASS, counted with cuobjdump): gl_add 7, gl_add_weak 5, gl_sub 5, gl_mul 18,
+// gl_canon 5.
+#pragma once
+#include <cstdint>
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+#define GL_P 0xFFFFFFFF00000001ull
+#define GL_EPS 0xFFFFFFFFull /* 2^64 mod p */
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ u64 gl_pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+
+// [0, 2^64) -> [0, p).  a >= p  <=>  a + EPS carries out of 64 bits, and then a - p = a + EPS mod 2^64.
+__device__ __forceinline__ u64 gl_canon(u64 a) {
+    u32 lo, hi, m;
+    asm("{\n\t"
+        ".reg .u32 l2, h2;\n\t"
+        "add.cc.u32 l2,%3,0xffffffff;\n\t"
+        "addc.cc.u32 h2,%4,0;\n\t"
+        "subc.u32 %2,0,0;\n\t" /* m = carry ? 0xffffffff : 0 */
+        "lop3.b32 %0,%3,l2,%2,0xD8;\n\t" /* m ? l2 : lo */
+        "lop3.b32 %1,%4,h2,%2,0xD8;\n\t"
+        "}"
+        : "=r"(lo), "=r"(hi), "=r"(m)
+        : "r"((u32)a), "r"((u32)(a >> 32)));
+    return gl_pack(lo, hi);
+}
+
+// weak add: a, b any u64 with a + b < 2^64 + p (e.g. one of them canonical) -> any u64.
+// One wrap correction: 2^64 = EPS (mod p).
+__device__ __forceinline__ u64 gl_add_weak(u64 a, u64 b) {
+    u32 lo, hi, m;
+    asm("{\n\t"
+        "add.cc.u32 %0,%3,%5;\n\t"
+        "addc.cc.u32 %1,%4,%6;\n\t"
+        "subc.u32 %2,0,0;\n\t" /* m = carry ? 0xffffffff : 0 */
+        "add.cc.u32 %0,%0,%2;\n\t"
+        "addc.u32 %1,%1,0;\n\t"
+        "}"
+        : "=r"(lo), "=r"(hi), "=r"(m)
+        : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return gl_pack(lo, hi);
+}
+
+// sub: a any u64, b < p -> any u64; a, b both canonical -> canonical (a - b + p on borrow).
+__device__ __forceinline__ u64 gl_sub(u64 a, u64 b) {
+    u32 lo, hi, m;
+    asm("{\n\t"
+        "sub.cc.u32 %0,%3,%5;\n\t"
+        "subc.cc.u32 %1,%4,%6;\n\t"
+        "subc.u32 %2,0,0;\n\t" /* m = borrow ? 0xffffffff : 0 */
+        "sub.cc.u32 %0,%0,%2;\n\t"
+        "subc.u32 %1,%1,0;\n\t"
+        "}"
+        : "=r"(lo), "=r"(hi), "=r"(m)
+        : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return gl_pack(lo, hi);
+}
+
+// canonical add: a, b < p -> a + b mod p in [0, p), computed as a - (p - b) like the reference
+// (b_field_element.rs:716-731).
+__device__ __forceinline__ u64 gl_add(u64 a, u64 b) { return gl_sub(a, GL_P - b); }
+
+// 64x64 -> 128 bit product as four 32-bit limbs. ptxas fuses the mad.lo.cc/madc.hi pairs into
+// IMAD.WIDE.U32 with carry-out: 4 IMAD.WIDE + 4 moves.
+__device__ __forceinline__ void gl_mul128(u64 a, u64 b, u32 &r0, u32 &r1, u32 &r2, u32 &r3) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    asm("{\n\t"
+        "mul.lo.u32 %0,%4,%6;\n\t"
+        "mul.hi.u32 %1,%4,%6;\n\t"
+        "mad.lo.cc.u32 %1,%4,%7,%1;\n\t"
+        "madc.hi.u32 %2,%4,%7,0;\n\t"
+        "mad.lo.cc.u32 %1,%5,%6,%1;\n\t"
+        "madc.hi.cc.u32 %2,%5,%6,%2;\n\t"
+        "addc.u32 %3,0,0;\n\t"
+        "mad.lo.cc.u32 %2,%5,%7,%2;\n\t"
+        "madc.hi.u32 %3,%5,%7,%3;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+
+// Solinas reduction of r0 + r1 2^32 + r2 2^64 + r3 2^96 using 2^64 = 2^32 - 1, 2^96 = -1 (mod p)
+// -> any u64.  x0 - r3 (one borrow fix) + r2 * EPS (one carry fix); neither fix can wrap twice.
+__device__ __forceinline__ u64 gl_reduce128(u32 r0, u32 r1, u32 r2, u32 r3) {
+    u32 lo, hi, m;
+    asm("{\n\t"
+        "sub.cc.u32  %0, %3, %6;\n\t"
+        "subc.cc.u32 %1, %4, 0;\n\t"
+        "subc.u32    %2, 0, 0;\n\t"
+        "sub.cc.u32  %0, %0, %2;\n\t"
+        "subc.u32    %1, %1, 0;\n\t"
+        "mad.lo.cc.u32  %0, %5, 0xffffffff, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, 0xffffffff, %1;\n\t"
+        "subc.u32    %2, 0, 0;\n\t"
+        "add.cc.u32  %0, %0, %2;\n\t"
+        "addc.u32    %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(lo), "=&r"(hi), "=&r"(m)
+        : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
+    return gl_pack(lo, hi);
+}
+
+// a * b mod p; a, b any u64 -> any u64
+__device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {
+    u32 r0, r1, r2, r3;
+    gl_mul128(a, b, r0, r1, r2, r3);
+    return gl_reduce128(r0, r1, r2, r3);
+}
+
+// canonical product
+__device__ __forceinline__ u64 gl_mulc(u64 a, u64 b) { return gl_canon(gl_mul(a, b)); }
+
+// 96-bit value x0 + x1 2^64 (x1 < 2^32) -> any u64
+__device__ __forceinline__ u64 gl_reduce96(u64 x0, u32 x1) {
+    u32 lo, hi, m;
+    asm("{\n\t"
+        "mad.lo.cc.u32  %0, %5, 0xffffffff, %3;\n\t"
+        "madc.hi.cc.u32 %1, %5, 0xffffffff, %4;\n\t"
+        "subc.u32    %2, 0, 0;\n\t"
+        "add.cc.u32  %0, %0, %2;\n\t"
+        "addc.u32    %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(lo), "=&r"(hi), "=&r"(m)
+        : "r"((u32)x0), "r"((u32)(x0 >> 32)), "r"(x1));
+    return gl_pack(lo, hi);
+}
+
+#endif  // __CUDACC__
+
+// ---- host-side helpers (table construction only) -----------------------------------------------
+static inline u64 hgl_mul(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) % GL_P); }
+static inline u64 hgl_pow(u64 base, u64 e) {
+    u64 acc = 1;
+    base %= GL_P;
+    while (e) {
+        if (e & 1) acc = hgl_mul(acc, base);
+        base = hgl_mul(base, base);
+        e >>= 1;
+    }
+    return acc;
+}
+static inline u64 hgl_inv(u64 a) { return hgl_pow(a, GL_P - 2); }
+// raw Montgomery word -> canonical value: v = raw * 2^-64 mod p
+static inline u64 hgl_from_raw(u64 raw) { return hgl_mul(raw % GL_P, hgl_inv(GL_EPS)); }
+static inline u64 hgl_to_raw(u64 v) { return hgl_mul(v % GL_P, GL_EPS); }
+// omega_n = 7^((p-1)/n), n = 2^log2n (matches PRIMITIVE_ROOTS, b_field_element.rs:43-78; checked in tests)
+static inline u64 hgl_root_of_unity(unsigned log2n) { return hgl_pow(7, (GL_P - 1) >> log2n); }

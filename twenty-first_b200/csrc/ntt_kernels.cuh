@@ -1,0 +1,347 @@
+// ntt_kernels.cuh -- batched Goldilocks NTT / iNTT (K1, K2 of SURVEY.md), generic multi-pass path.
+//
+// Replaces math::ntt::{ntt, intt, ntt_unchecked, unscale} (twenty-first/src/math/ntt.rs:67-82,
+// 109-125, 153-228) and the scale / zero-pad steps of Polynomial::fast_coset_{evaluate,interpolate}
+// (math/polynomial.rs:760-773, 1374-1399, 1907-1918).
+//
+// Functional spec: for every array of the batch and every coefficient lane
+// c < w, y[i][c] = sum_j x[j][c] * omega_n^(i j) mod p on the raw words, natural order in and out,
+// omega_n = 7^((p-1)/n) (PRIMITIVE_ROOTS, b_field_element.rs:43-78).  The reference does a
+// bit-reversal pass plus log2(n) radix-2 DIT passes over memory; here the transform is split into
+// k = ceil(log2 n / 10) passes of at most 1024 points each (digit decomposition of the index):
+//
+//   input index  j = j_1 (N_2..N_k) + j_2 (N_3..N_k) + ... + j_k
+//   output index i = i_1 + N_1 i_2 + N_1 N_2 i_3 + ...
+//
+//   column pass p < k : position preserving; view [outer][N_p][inner = N_{p+1}..N_k][w], DFT along
+//                       N_p for a tile of 16 consecutive words of the inner axis (128 B segments),
+//                       then multiply by omega_{N_p inner}^(i_p * j_rest).
+//   row pass (last)   : DFT along the contiguous N_k axis for TO rows that differ in i_1, stored
+//                       transposed so that consecutive i_1 are consecutive in memory.
+//
+// Inside a CTA the DFT is an in-shared-memory radix-2 DIF (natural in, bit-reversed out; the
+// un-reversal is folded into the store).  All arithmetic is canonical mod p.
+//
+// HBM layout: arrays are dense, n*w words each, AoS for w = 3 (x_field_element.rs:56-59).  A
+// scratch buffer of the same size carries the data between passes.
+#pragma once
+#include "runtime.cuh"
+
+namespace tf21 {
+
+constexpr u32 kNttMaxLogPass = 10;  // at most 1024 points per pass
+constexpr u32 kNttColTile = 16;     // words per row segment in a column pass (128 B)
+constexpr u32 kNttColStride = 17;   // padded shared-memory row stride (odd => conflict free)
+
+struct ScaleTab {  // factor(idx) = lo[idx & (2^h - 1)] * hi[idx >> h]; lo == nullptr => none
+    const u64 *lo;
+    const u64 *hi;
+    u32 h;
+};
+
+__device__ __forceinline__ u64 scale_factor(const ScaleTab &t, u64 idx) {
+    return gl_mulc(t.lo[idx & ((1ull << t.h) - 1)], t.hi[idx >> t.h]);
+}
+
+// shared-memory row padding: one spare row every 32 so that bit-reversed row reads spread over banks
+__device__ __forceinline__ u32 rowp(u32 r) { return r + (r >> 5); }
+
+__device__ __forceinline__ u32 bitrev(u32 v, u32 bits) { return __brev(v) >> (32 - bits); }
+
+// radix-2 DIF over the rows of tile[rowp(r) * stride + c], c < ncol.  Natural in, bit-reversed out.
+// tw[e] = omega_{np}^e, e < np/2.   (butterfly of ntt.rs:203-210 in decimation-in-frequency form)
+__device__ __forceinline__ void dft_dif_smem(u64 *tile, u32 stride, u32 ncol, u32 log_np, const u64 *tw) {
+    const u32 items = (1u << (log_np - 1)) * ncol;
+    for (u32 s = 0; s < log_np; s++) {
+        const u32 lh = log_np - 1 - s;
+        for (u32 it = threadIdx.x; it < items; it += blockDim.x) {
+            u32 c = it % ncol, bf = it / ncol;
+            u32 pos = bf & ((1u << lh) - 1), grp = bf >> lh;
+            u32 r0 = (grp << (lh + 1)) + pos, r1 = r0 + (1u << lh);
+            u64 *p0 = tile + rowp(r0) * stride + c;
+            u64 *p1 = tile + rowp(r1) * stride + c;
+            u64 u = *p0, v = *p1;
+            *p0 = gl_add(u, v);
+            *p1 = gl_mulc(gl_sub(u, v), tw[pos << s]);
+        }
+        __syncthreads();
+    }
+}
+
+struct ColPassArgs {
+    const u64 *src;
+    u64 *dst;
+    u64 src_array_words, dst_array_words;
+    u32 log_np, w;
+    u64 inner_words;  // inner elements * w = row stride in words
+    u32 n_col_tiles, n_outer;
+    u64 n_in_elems;   // elements with index >= n_in_elems read as zero (zero extension, pass 1 only)
+    const u64 *tw_np;
+    ScaleTab tw;      // omega_B^e, B = N_p * inner
+    u32 log_b;
+    ScaleTab pre;     // optional per-element scale on load, indexed by the element index in the array
+};
+
+__global__ void ntt_col_pass_kernel(const ColPassArgs a) {
+    extern __shared__ u64 smem[];
+    const u32 np = 1u << a.log_np;
+    u64 *tile = smem;
+    u64 *twsm = smem + (size_t)(np + (np >> 5) + 1) * kNttColStride;
+    const u32 ct = blockIdx.x % a.n_col_tiles;
+    const u32 rest = blockIdx.x / a.n_col_tiles;
+    const u32 o = rest % a.n_outer, b = rest / a.n_outer;
+    const u64 q0 = (u64)ct * kNttColTile;
+    const u32 ncols = (u32)min((u64)kNttColTile, a.inner_words - q0);
+    const u64 inner_elems = a.inner_words / a.w;
+
+    for (u32 i = threadIdx.x; i < (np >> 1); i += blockDim.x) twsm[i] = a.tw_np[i];
+
+    const u64 block_off = (u64)o * np * a.inner_words + q0;
+    const u64 *src = a.src + (u64)b * a.src_array_words + block_off;
+    for (u32 idx = threadIdx.x; idx < np * kNttColTile; idx += blockDim.x) {
+        u32 r = idx / kNttColTile, c = idx % kNttColTile;
+        u64 v = 0;
+        if (c < ncols) {
+            u64 j = ((u64)o * np + r) * inner_elems + (q0 + c) / a.w;
+            if (j < a.n_in_elems) {
+                v = gl_canon(src[(u64)r * a.inner_words + c]);
+                if (a.pre.lo) v = gl_mulc(v, scale_factor(a.pre, j));
+            }
+        }
+        tile[rowp(r) * kNttColStride + c] = v;
+    }
+    __syncthreads();
+
+    dft_dif_smem(tile, kNttColStride, kNttColTile, a.log_np, twsm);
+
+    u64 *dst = a.dst + (u64)b * a.dst_array_words + block_off;
+    const u64 bmask = (1ull << a.log_b) - 1;
+    for (u32 idx = threadIdx.x; idx < np * kNttColTile; idx += blockDim.x) {
+        u32 ip = idx / kNttColTile, c = idx % kNttColTile;
+        if (c < ncols) {
+            u64 v = tile[rowp(bitrev(ip, a.log_np)) * kNttColStride + c];
+            u64 jrest = (q0 + c) / a.w;
+            u64 e = ((u64)ip * jrest) & bmask;
+            dst[(u64)ip * a.inner_words + c] = gl_mulc(v, scale_factor(a.tw, e));
+        }
+    }
+}
+
+struct RowPassArgs {
+    const u64 *src;
+    u64 *dst;
+    u64 src_array_words, dst_array_words;
+    u32 log_nk, w, to;       // to = rows per tile
+    u32 n_tiles_t, mid;      // tiles along the t axis; number of `mid` values (1 unless 3 passes)
+    u32 rows_total;          // N_1 (multi pass) or batch (single pass)
+    u32 single;              // 1: single-pass mode (rows are whole arrays of the batch)
+    u64 src_t_stride;        // words between consecutive rows of a tile in src
+    u64 dst_t_stride, dst_i_stride, dst_mid_stride;
+    u64 elem_i_stride, elem_mid_stride;  // output element index = t (multi) + mid*.. + i_k * elem_i_stride
+    u64 n_in_elems;          // single-pass zero extension
+    const u64 *tw_nk;
+    ScaleTab pre;            // single-pass only (indexed by input element index)
+    ScaleTab post;           // indexed by output element index
+    u64 post_scalar;         // 0 => none ; else multiply every output by it (n^-1 for intt)
+};
+
+__global__ void ntt_row_pass_kernel(const RowPassArgs a) {
+    extern __shared__ u64 smem[];
+    const u32 nk = 1u << a.log_nk;
+    const u32 ncol = a.to * a.w;
+    const u32 stride = ncol | 1;
+    u64 *tile = smem;
+    u64 *twsm = smem + (size_t)(nk + (nk >> 5) + 1) * stride;
+    const u32 tt = blockIdx.x % a.n_tiles_t;
+    const u32 rest = blockIdx.x / a.n_tiles_t;
+    const u32 mid = rest % a.mid, b = rest / a.mid;
+    const u32 t0 = tt * a.to;
+    const u32 rows_valid = min(a.to, a.rows_total - t0);
+    const u32 row_words = nk * a.w;
+
+    for (u32 i = threadIdx.x; i < (nk >> 1); i += blockDim.x) twsm[i] = a.tw_nk[i];
+
+    const u64 *src = a.src + (u64)b * a.src_array_words + (u64)t0 * a.src_t_stride + (u64)mid * row_words;
+    for (u32 idx = threadIdx.x; idx < a.to * row_words; idx += blockDim.x) {
+        u32 t = idx / row_words, rw = idx % row_words;
+        u32 r = rw / a.w, lane = rw % a.w;
+        u64 v = 0;
+        if (t < rows_valid && (u64)r < a.n_in_elems) {
+            v = gl_canon(src[(u64)t * a.src_t_stride + rw]);
+            if (a.pre.lo) v = gl_mulc(v, scale_factor(a.pre, r));
+        }
+        tile[rowp(r) * stride + t * a.w + lane] = v;
+    }
+    __syncthreads();
+
+    dft_dif_smem(tile, stride, ncol, a.log_nk, twsm);
+
+    u64 *dst = a.dst + (u64)b * a.dst_array_words + (u64)t0 * a.dst_t_stride + (u64)mid * a.dst_mid_stride;
+    const u64 elem_base = (a.single ? 0 : (u64)t0) + (u64)mid * a.elem_mid_stride;
+    if (!a.single) {
+        // consecutive (t, lane) are consecutive in memory
+        for (u32 idx = threadIdx.x; idx < nk * ncol; idx += blockDim.x) {
+            u32 ik = idx / ncol, cc = idx % ncol;
+            u32 t = cc / a.w;
+            if (t < rows_valid) {
+                u64 v = tile[rowp(bitrev(ik, a.log_nk)) * stride + cc];
+                if (a.post_scalar) v = gl_mulc(v, a.post_scalar);
+                if (a.post.lo) v = gl_mulc(v, scale_factor(a.post, elem_base + t + (u64)ik * a.elem_i_stride));
+                dst[(u64)ik * a.dst_i_stride + cc] = v;
+            }
+        }
+    } else {
+        // consecutive (i_k, lane) are consecutive in memory
+        for (u32 idx = threadIdx.x; idx < a.to * row_words; idx += blockDim.x) {
+            u32 t = idx / row_words, rw = idx % row_words;
+            u32 ik = rw / a.w, lane = rw % a.w;
+            if (t < rows_valid) {
+                u64 v = tile[rowp(bitrev(ik, a.log_nk)) * stride + t * a.w + lane];
+                if (a.post_scalar) v = gl_mulc(v, a.post_scalar);
+                if (a.post.lo) v = gl_mulc(v, scale_factor(a.post, (u64)ik));
+                dst[(u64)t * a.dst_t_stride + rw] = v;
+            }
+        }
+    }
+}
+
+// ---- host planning ------------------------------------------------------------------------------
+
+inline size_t col_pass_smem(u32 log_np) {
+    u32 np = 1u << log_np;
+    return ((size_t)(np + (np >> 5) + 1) * kNttColStride + (np >> 1)) * sizeof(u64);
+}
+inline size_t row_pass_smem(u32 log_nk, u32 to, u32 w) {
+    u32 nk = 1u << log_nk;
+    u32 stride = (to * w) | 1;
+    return ((size_t)(nk + (nk >> 5) + 1) * stride + (nk >> 1)) * sizeof(u64);
+}
+inline u32 pick_threads(u64 items) {
+    u32 nt = 64;
+    while (nt < 1024 && (u64)nt * 8 < items) nt <<= 1;
+    return nt;
+}
+
+struct NttPlan {
+    u32 k;
+    u32 l[4];
+};
+
+inline NttPlan make_plan(u32 log_n) {
+    NttPlan p{};
+    p.k = (log_n + kNttMaxLogPass - 1) / kNttMaxLogPass;
+    if (p.k == 0) p.k = 1;
+    for (u32 i = 0; i < p.k; i++) p.l[i] = log_n / p.k + (i < log_n % p.k ? 1 : 0);
+    return p;
+}
+
+// Core entry: dst[b] = scale_post( NTT_n( zero_extend( scale_pre( src[b][0..n_in) ) ) ) ) for b < batch.
+// src arrays are n_in*w words apart, dst arrays n*w words apart.  src == dst is allowed when
+// n_in == n.  `scratch` (n*w*batch words) is required when log2 n > 10.
+inline int ntt_run(DeviceTables &tabs, const u64 *src, u64 n_in, u64 *dst, u64 n, u32 w, u64 batch, int inverse,
+                   ScaleTab pre, ScaleTab post, u64 post_scalar, u64 *scratch, cudaStream_t st) {
+    const u32 log_n = ilog2_u64(n);
+    const NttPlan plan = make_plan(log_n);
+    const u64 array_words = n * w;
+    const u64 src_array_words = n_in * w;
+    const u64 *tw_small = tabs.tw_small[inverse ? 1 : 0];
+
+    const u64 *cur_src = src;
+    u64 cur_src_words = src_array_words;
+    u64 cur_n_in = n_in;
+    ScaleTab cur_pre = pre;
+    u32 consumed = 0;  // log2 of N_1..N_{p-1}
+    for (u32 p = 0; p + 1 < plan.k; p++) {
+        ColPassArgs a{};
+        a.src = cur_src;
+        a.dst = scratch;
+        a.src_array_words = cur_src_words;
+        a.dst_array_words = array_words;
+        a.log_np = plan.l[p];
+        a.w = w;
+        const u32 log_inner = log_n - consumed - plan.l[p];
+        a.inner_words = ((u64)1 << log_inner) * w;
+        a.n_col_tiles = (u32)((a.inner_words + kNttColTile - 1) / kNttColTile);
+        a.n_outer = 1u << consumed;
+        a.n_in_elems = cur_n_in;
+        a.tw_np = tw_small + ((1u << plan.l[p]) >> 1) - 1;
+        a.log_b = log_n - consumed;
+        DeviceTables::Split sp;
+        TF21_TRY(get_split_tables(tabs, a.log_b, inverse, &sp));
+        a.tw = ScaleTab{sp.lo, sp.hi, sp.h};
+        a.pre = cur_pre;
+        u64 grid = batch * a.n_outer * a.n_col_tiles;
+        if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+        u32 nt = pick_threads((u64)(1u << plan.l[p]) / 2 * kNttColTile);
+        TF21_LAUNCH(ntt_col_pass_kernel, (unsigned)grid, nt, col_pass_smem(plan.l[p]), st, a);
+        consumed += plan.l[p];
+        cur_src = scratch;
+        cur_src_words = array_words;
+        cur_n_in = n;
+        cur_pre = ScaleTab{nullptr, nullptr, 0};
+    }
+
+    RowPassArgs r{};
+    r.src = cur_src;
+    r.dst = dst;
+    r.src_array_words = cur_src_words;
+    r.dst_array_words = array_words;
+    r.log_nk = plan.l[plan.k - 1];
+    r.w = w;
+    const u32 nk = 1u << r.log_nk;
+    // rows per tile: keep the tile under ~150 KB of shared memory
+    u32 to = 16;
+    while (to > 1 && row_pass_smem(r.log_nk, to, w) > 150 * 1024) to--;
+    r.tw_nk = tw_small + (nk >> 1) - 1;
+    r.post = post;
+    r.post_scalar = post_scalar;
+    u64 grid;
+    if (plan.k == 1) {
+        r.single = 1;
+        if (batch > 0xffffffffull) return TF21_E_LEN_TOO_LARGE;
+        r.rows_total = (u32)batch;
+        if ((u64)to > batch) to = (u32)batch;
+        r.to = to;
+        r.n_tiles_t = (u32)((batch + to - 1) / to);
+        r.mid = 1;
+        r.src_t_stride = cur_src_words;
+        r.dst_t_stride = array_words;
+        r.dst_i_stride = w;
+        r.dst_mid_stride = 0;
+        r.elem_i_stride = 1;
+        r.elem_mid_stride = 0;
+        r.n_in_elems = cur_n_in;
+        r.pre = cur_pre;
+        // the batch index is folded into the t axis: arrays are addressed through t strides
+        r.src_array_words = 0;
+        r.dst_array_words = 0;
+        grid = r.n_tiles_t;
+    } else {
+        r.single = 0;
+        const u32 n1 = 1u << plan.l[0];
+        const u32 midc = (plan.k == 3) ? (1u << plan.l[1]) : 1u;
+        if (to > n1) to = n1;
+        // to must divide N_1 (power of two) so tiles never straddle
+        while (n1 % to) to--;
+        r.to = to;
+        r.rows_total = n1;
+        r.n_tiles_t = n1 / to;
+        r.mid = midc;
+        r.src_t_stride = (u64)midc * nk * w;       // consecutive i_1
+        r.dst_t_stride = w;
+        const u64 o_total = n >> r.log_nk;          // N_1 .. N_{k-1}
+        r.dst_i_stride = o_total * w;
+        r.dst_mid_stride = (u64)n1 * w;             // o' = i_1 + N_1 * i_2
+        r.elem_i_stride = o_total;
+        r.elem_mid_stride = n1;
+        r.n_in_elems = nk;
+        r.pre = ScaleTab{nullptr, nullptr, 0};
+        grid = batch * r.n_tiles_t * r.mid;
+    }
+    if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+    u32 nt = pick_threads((u64)nk / 2 * r.to * w);
+    TF21_LAUNCH(ntt_row_pass_kernel, (unsigned)grid, nt, row_pass_smem(r.log_nk, r.to, w), st, r);
+    return 0;
+}
+
+}  // namespace tf21

@@ -1,0 +1,449 @@
+// tf21.cu -- the C ABI of libtf21 (include/tf21.h): argument checking, device state, host<->device
+// staging, and dispatch into the sm_100a kernels.  Single translation unit (the kernels live in the
+// included .cuh files) so the __constant__ tables are shared without relocatable device code.
+#include "ntt_kernels.cuh"
+#include "tip5_kernels.cuh"
+
+using namespace tf21;
+
+namespace tf21 {
+
+// per-device state, created on first use of a device
+static int get_tables(DeviceTables **out) {
+    int dev;
+    TF21_TRY(current_device(&dev));
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceTables &t = g_devices[dev];
+    if (!t.constants_ready) {
+        cudaDeviceProp prop;
+        TF21_CUDA(cudaGetDeviceProperties(&prop, dev));
+        t.sm_count = prop.multiProcessorCount;
+        t.smem_optin = prop.sharedMemPerBlockOptin;
+        TF21_TRY(upload_tip5_constants());
+        for (int inv = 0; inv < 2; inv++) {
+            std::vector<u64> tw((1u << kNttMaxLogPass) - 1);
+            for (u32 l = 1; l <= kNttMaxLogPass; l++) {
+                u64 w = hgl_root_of_unity(l);
+                if (inv) w = hgl_inv(w);
+                u64 acc = 1;
+                u64 *dst = tw.data() + ((1u << l) >> 1) - 1;
+                for (u32 e = 0; e < (1u << l) / 2; e++) {
+                    dst[e] = acc;
+                    acc = hgl_mul(acc, w);
+                }
+            }
+            TF21_TRY(upload(t, tw, &t.tw_small[inv]));
+        }
+        TF21_CUDA(cudaFuncSetAttribute(ntt_col_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)t.smem_optin));
+        TF21_CUDA(cudaFuncSetAttribute(ntt_row_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)t.smem_optin));
+        t.constants_ready = true;
+    }
+    *out = &t;
+    return 0;
+}
+
+static int check_ntt_len(u64 n, u32 width) {
+    if (width != 1 && width != 3) return TF21_E_BAD_ARG;
+    if (n > 0xffffffffull) return TF21_E_LEN_TOO_LARGE;          // ntt.rs:135-136
+    if (n != 0 && (n & (n - 1)) != 0) return TF21_E_LEN_NOT_POW2; // ntt.rs:137
+    if (n > (1ull << 30)) return TF21_E_LEN_TOO_LARGE;           // device implementation limit
+    return 0;
+}
+
+// stream-ordered scratch
+struct Scratch {
+    u64 *p = nullptr;
+    cudaStream_t st;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    int alloc(u64 words) {
+        if (words == 0) return 0;
+        TF21_CUDA(cudaMallocAsync((void **)&p, words * sizeof(u64), st));
+        return 0;
+    }
+    ~Scratch() {
+        if (p) cudaFreeAsync(p, st);
+    }
+};
+
+// table builders take the mutex themselves
+static int split_locked(DeviceTables &t, u64 g, u64 c0, u64 count, ScaleTab *out) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceTables::Split s;
+    TF21_TRY(get_scale_tables(t, g, c0, count, &s));
+    *out = ScaleTab{s.lo, s.hi, s.h};
+    return 0;
+}
+
+static int ntt_run_locked(DeviceTables &t, const u64 *src, u64 n_in, u64 *dst, u64 n, u32 w, u64 batch, int inverse,
+                          ScaleTab pre, ScaleTab post, u64 post_scalar, cudaStream_t st) {
+    if (n <= 1) {  // identity transform (ntt.rs:178-181 returns early; len 1 has no stages)
+        if (n == 1 && src != dst && n_in >= 1)
+            TF21_CUDA(cudaMemcpyAsync(dst, src, batch * w * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        if (n == 1 && n_in == 0) TF21_CUDA(cudaMemsetAsync(dst, 0, batch * w * sizeof(u64), st));
+        return 0;
+    }
+    Scratch scratch(st);
+    if (ilog2_u64(n) > kNttMaxLogPass) TF21_TRY(scratch.alloc(n * w * batch));
+    {
+        // split-table construction mutates the cache
+        std::lock_guard<std::mutex> lock(g_mutex);
+        NttPlan plan = make_plan(ilog2_u64(n));
+        u32 consumed = 0;
+        for (u32 p = 0; p + 1 < plan.k; p++) {
+            DeviceTables::Split sp;
+            TF21_TRY(get_split_tables(t, ilog2_u64(n) - consumed, inverse, &sp));
+            consumed += plan.l[p];
+        }
+    }
+    return ntt_run(t, src, n_in, dst, n, w, batch, inverse, pre, post, post_scalar, scratch.p, st);
+}
+
+}  // namespace tf21
+
+#define NO_SCALE (ScaleTab{nullptr, nullptr, 0})
+
+extern "C" {
+
+int tf21_init(int device) {
+    TF21_CUDA(cudaSetDevice(device));
+    DeviceTables *t;
+    return get_tables(&t);
+}
+
+int tf21_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (auto &kv : g_devices) {
+        cudaSetDevice(kv.first);
+        cudaDeviceSynchronize();
+        for (void *p : kv.second.owned) cudaFree(p);
+    }
+    g_devices.clear();
+    if (prev >= 0) cudaSetDevice(prev);
+    return 0;
+}
+
+const char *tf21_strerror(int code) {
+    switch (code) {
+        case TF21_OK: return "ok";
+        case TF21_E_LEN_NOT_POW2: return "slice length must be 0 or a power of two (ntt.rs:137)";
+        case TF21_E_LEN_TOO_LARGE: return "slice should be no longer than u32::MAX (ntt.rs:135); device limit 2^30";
+        case TF21_E_TOO_FEW_LEAFS: return "MerkleTreeError::TooFewLeafs";
+        case TF21_E_INCORRECT_NUMBER_OF_LEAFS: return "MerkleTreeError::IncorrectNumberOfLeafs";
+        case TF21_E_ORDER_LE_DEGREE:
+            return "`Polynomial::fast_coset_evaluate` is currently limited to domains of order greater than the "
+                   "degree of the polynomial.";
+        case TF21_E_ALLOC: return "allocation failed (MerkleTreeError::TreeTooHigh)";
+        case TF21_E_CUDA: return "CUDA error (see tf21_last_cuda_error)";
+        case TF21_E_BAD_ARG: return "bad argument";
+        default: return "unknown tf21 error";
+    }
+}
+
+const char *tf21_last_cuda_error(void) { return g_last_cuda_error; }
+uint64_t tf21_kernel_launch_count(void) { return g_launches.load(); }
+
+int tf21_malloc(void **dptr, uint64_t bytes) {
+    TF21_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return 0;
+}
+int tf21_free(void *dptr) {
+    TF21_CUDA(cudaFree(dptr));
+    return 0;
+}
+int tf21_memcpy_h2d(void *dst, const void *src, uint64_t bytes, tf21_stream_t stream) {
+    TF21_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+int tf21_memcpy_d2h(void *dst, const void *src, uint64_t bytes, tf21_stream_t stream) {
+    TF21_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+int tf21_stream_sync(tf21_stream_t stream) {
+    TF21_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+// ---- NTT -------------------------------------------------------------------------------------------
+int tf21_ntt_dev(uint64_t *d_data, uint64_t n, uint32_t width, uint64_t batch, int inverse, tf21_stream_t stream) {
+    TF21_TRY(check_ntt_len(n, width));
+    if (n <= 1 || batch == 0) return 0;
+    if (!d_data) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    u64 post_scalar = inverse ? hgl_inv(n % GL_P) : 0;  // unscale, ntt.rs:220-228
+    return ntt_run_locked(*t, d_data, n, d_data, n, width, batch, inverse, NO_SCALE, NO_SCALE, post_scalar,
+                          (cudaStream_t)stream);
+}
+
+// host staging helper: device buffer with H2D on construction side and D2H on demand
+struct DevBuf {
+    u64 *p = nullptr;
+    int alloc(u64 words) {
+        TF21_CUDA(cudaMalloc((void **)&p, (words ? words : 1) * sizeof(u64)));
+        return 0;
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+static int host_ntt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch, int inverse) {
+    TF21_TRY(check_ntt_len(n, width));
+    if (n <= 1 || batch == 0) return 0;
+    if (!data) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    u64 words = n * width * batch;
+    DevBuf buf;
+    TF21_TRY(buf.alloc(words));
+    TF21_CUDA(cudaMemcpy(buf.p, data, words * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_ntt_dev(buf.p, n, width, batch, inverse, nullptr));
+    TF21_CUDA(cudaMemcpy(data, buf.p, words * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tf21_ntt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch) { return host_ntt(data, n, width, batch, 0); }
+int tf21_intt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch) { return host_ntt(data, n, width, batch, 1); }
+
+// ---- coset -----------------------------------------------------------------------------------------
+int tf21_coset_evaluate_dev(const uint64_t *d_coeffs, uint64_t n_coeffs, uint32_t width, uint64_t offset_raw,
+                            uint64_t order, uint64_t *d_out, tf21_stream_t stream) {
+    TF21_TRY(check_ntt_len(order, width));
+    if (n_coeffs > order) return TF21_E_ORDER_LE_DEGREE;  // polynomial.rs:1388-1392
+    if (order == 0) return 0;
+    if (!d_out || (n_coeffs && !d_coeffs)) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_coeffs == 0) {
+        TF21_CUDA(cudaMemsetAsync(d_out, 0, order * width * sizeof(u64), st));
+        return 0;
+    }
+    // c_i * offset^i (Polynomial::scale, polynomial.rs:760-773) on load, zero padding to `order`
+    u64 g = hgl_from_raw(offset_raw);
+    ScaleTab pre;
+    TF21_TRY(split_locked(*t, g, 1, n_coeffs, &pre));
+    return ntt_run_locked(*t, d_coeffs, n_coeffs, d_out, order, width, 1, 0, pre, NO_SCALE, 0, st);
+}
+
+int tf21_coset_interpolate_dev(const uint64_t *d_values, uint64_t n, uint32_t width, uint64_t offset_raw,
+                               uint64_t *d_coeffs_out, tf21_stream_t stream) {
+    TF21_TRY(check_ntt_len(n, width));
+    if (n == 0) return 0;
+    if (!d_values || !d_coeffs_out) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    // u = iNTT(values); c_i = u_i * offset^-i  (polynomial.rs:1912-1917); n^-1 folded into the table
+    u64 g_inv = hgl_inv(hgl_from_raw(offset_raw));  // offset.inverse() panics on zero in the reference
+    ScaleTab post;
+    TF21_TRY(split_locked(*t, g_inv, hgl_inv(n % GL_P), n, &post));
+    if (n == 1) {
+        TF21_CUDA(cudaMemcpyAsync(d_coeffs_out, d_values, width * sizeof(u64), cudaMemcpyDeviceToDevice,
+                                  (cudaStream_t)stream));
+        return 0;
+    }
+    return ntt_run_locked(*t, d_values, n, d_coeffs_out, n, width, 1, 1, NO_SCALE, post, 0, (cudaStream_t)stream);
+}
+
+int tf21_coset_lde_dev(const uint64_t *d_values, uint64_t n_in, uint64_t offset_in_raw, uint64_t n_out,
+                       uint64_t offset_out_raw, uint32_t width, uint64_t *d_out, tf21_stream_t stream) {
+    TF21_TRY(check_ntt_len(n_in, width));
+    TF21_TRY(check_ntt_len(n_out, width));
+    if (n_in == 0 || n_out < n_in) return TF21_E_BAD_ARG;
+    if (!d_values || !d_out) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    cudaStream_t st = (cudaStream_t)stream;
+    // coefficients c_i = iNTT(v)_i * n_in^-1 * (g_out / g_in)^i, then zero-extended NTT of size n_out
+    u64 ratio = hgl_mul(hgl_from_raw(offset_out_raw), hgl_inv(hgl_from_raw(offset_in_raw)));
+    Scratch coeffs(st);
+    TF21_TRY(coeffs.alloc(n_in * width));
+    if (n_in == 1) {
+        TF21_CUDA(cudaMemcpyAsync(coeffs.p, d_values, width * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    } else {
+        ScaleTab post;
+        TF21_TRY(split_locked(*t, ratio, hgl_inv(n_in % GL_P), n_in, &post));
+        TF21_TRY(ntt_run_locked(*t, d_values, n_in, coeffs.p, n_in, width, 1, 1, NO_SCALE, post, 0, st));
+    }
+    return ntt_run_locked(*t, coeffs.p, n_in, d_out, n_out, width, 1, 0, NO_SCALE, NO_SCALE, 0, st);
+}
+
+int tf21_coset_evaluate(const uint64_t *coeffs, uint64_t n_coeffs, uint32_t width, uint64_t offset_raw,
+                        uint64_t order, uint64_t *out) {
+    TF21_TRY(check_ntt_len(order, width));
+    // degree = index of the last non-zero coefficient (Polynomial::new strips trailing zeros)
+    u64 live = n_coeffs;
+    while (live > 0) {
+        bool nz = false;
+        for (u32 c = 0; c < width; c++) nz |= coeffs[(live - 1) * width + c] != 0;
+        if (nz) break;
+        live--;
+    }
+    if (!(order > live - 1 || live == 0)) return TF21_E_ORDER_LE_DEGREE;  // order > degree, :1388-1392
+    if (order == 0) return 0;
+    DevBuf in, outb;
+    TF21_TRY(in.alloc(live * width));
+    TF21_TRY(outb.alloc(order * width));
+    if (live) TF21_CUDA(cudaMemcpy(in.p, coeffs, live * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_coset_evaluate_dev(in.p, live, width, offset_raw, order, outb.p, nullptr));
+    TF21_CUDA(cudaMemcpy(out, outb.p, order * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tf21_coset_interpolate(const uint64_t *values, uint64_t n, uint32_t width, uint64_t offset_raw,
+                           uint64_t *coeffs_out) {
+    TF21_TRY(check_ntt_len(n, width));
+    if (n == 0) return 0;
+    DevBuf in, outb;
+    TF21_TRY(in.alloc(n * width));
+    TF21_TRY(outb.alloc(n * width));
+    TF21_CUDA(cudaMemcpy(in.p, values, n * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_coset_interpolate_dev(in.p, n, width, offset_raw, outb.p, nullptr));
+    TF21_CUDA(cudaMemcpy(coeffs_out, outb.p, n * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tf21_coset_lde(const uint64_t *values, uint64_t n_in, uint64_t offset_in_raw, uint64_t n_out,
+                   uint64_t offset_out_raw, uint32_t width, uint64_t *out) {
+    TF21_TRY(check_ntt_len(n_in, width));
+    TF21_TRY(check_ntt_len(n_out, width));
+    if (n_in == 0 || n_out < n_in) return TF21_E_BAD_ARG;
+    DevBuf in, outb;
+    TF21_TRY(in.alloc(n_in * width));
+    TF21_TRY(outb.alloc(n_out * width));
+    TF21_CUDA(cudaMemcpy(in.p, values, n_in * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_coset_lde_dev(in.p, n_in, offset_in_raw, n_out, offset_out_raw, width, outb.p, nullptr));
+    TF21_CUDA(cudaMemcpy(out, outb.p, n_out * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- Tip5 ------------------------------------------------------------------------------------------
+int tf21_tip5_permute_dev(uint64_t *d_states, uint64_t count, tf21_stream_t stream) {
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    return launch_permute(d_states, count, (cudaStream_t)stream);
+}
+int tf21_tip5_hash_10_dev(const uint64_t *d_in, uint64_t count, uint64_t *d_out, tf21_stream_t stream) {
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    return launch_hash10(d_in, count, d_out, (cudaStream_t)stream);
+}
+int tf21_tip5_hash_rows_dev(const uint64_t *d_rows, uint64_t row_len, uint64_t n_rows, uint64_t *d_out,
+                            tf21_stream_t stream) {
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    return launch_hash_rows(d_rows, row_len, n_rows, d_out, (cudaStream_t)stream);
+}
+
+int tf21_tip5_permute(uint64_t *states, uint64_t count) {
+    if (count == 0) return 0;
+    if (!states) return TF21_E_BAD_ARG;
+    DevBuf b;
+    TF21_TRY(b.alloc(16 * count));
+    TF21_CUDA(cudaMemcpy(b.p, states, 16 * count * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_tip5_permute_dev(b.p, count, nullptr));
+    TF21_CUDA(cudaMemcpy(states, b.p, 16 * count * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tf21_tip5_hash_10(const uint64_t *in, uint64_t count, uint64_t *out) {
+    if (count == 0) return 0;
+    if (!in || !out) return TF21_E_BAD_ARG;
+    DevBuf bi, bo;
+    TF21_TRY(bi.alloc(10 * count));
+    TF21_TRY(bo.alloc(5 * count));
+    TF21_CUDA(cudaMemcpy(bi.p, in, 10 * count * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_tip5_hash_10_dev(bi.p, count, bo.p, nullptr));
+    TF21_CUDA(cudaMemcpy(out, bo.p, 5 * count * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tf21_tip5_hash_pairs(const uint64_t *pairs, uint64_t count, uint64_t *out) {
+    return tf21_tip5_hash_10(pairs, count, out);  // hash_pair is hash_10 of left | right, tip5/mod.rs:577-586
+}
+
+int tf21_tip5_hash_rows(const uint64_t *rows, uint64_t row_len, uint64_t n_rows, uint64_t *out) {
+    if (n_rows == 0) return 0;
+    if (!out || (row_len && !rows)) return TF21_E_BAD_ARG;
+    DevBuf bi, bo;
+    TF21_TRY(bi.alloc(row_len * n_rows));
+    TF21_TRY(bo.alloc(5 * n_rows));
+    if (row_len) TF21_CUDA(cudaMemcpy(bi.p, rows, row_len * n_rows * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_tip5_hash_rows_dev(bi.p, row_len, n_rows, bo.p, nullptr));
+    TF21_CUDA(cudaMemcpy(out, bo.p, 5 * n_rows * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tf21_tip5_hash_varlen(const uint64_t *in, uint64_t len, uint64_t out[5]) {
+    return tf21_tip5_hash_rows(in, len, 1, out);
+}
+
+// ---- Merkle ----------------------------------------------------------------------------------------
+int tf21_merkle_build_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d_nodes_out, tf21_stream_t stream) {
+    TF21_TRY(check_leaf_count(n_leafs));
+    if (!d_leafs || !d_nodes_out) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    return merkle_build_dev(d_leafs, n_leafs, d_nodes_out, (cudaStream_t)stream);
+}
+
+int tf21_merkle_root_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d_root_out, tf21_stream_t stream) {
+    TF21_TRY(check_leaf_count(n_leafs));
+    if (!d_leafs || !d_root_out) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_leafs == 1) {
+        TF21_CUDA(cudaMemcpyAsync(d_root_out, d_leafs, 5 * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    // heap-indexed upper half only: upper[cnt..2cnt) for cnt <= n/2; the leaves are read in place
+    Scratch upper(st);
+    TF21_TRY(upper.alloc(5 * n_leafs));
+    u64 cnt = n_leafs / 2;
+    TF21_TRY(launch_hash10(d_leafs, cnt, upper.p + 5 * cnt, st));
+    if (cnt > 1) TF21_TRY(launch_merkle_levels(upper.p, cnt, st));
+    TF21_CUDA(cudaMemcpyAsync(d_root_out, upper.p + 5, 5 * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int tf21_merkle_scatter_subtree_dev(const uint64_t *d_local_nodes, uint64_t n_local_leafs, uint64_t shard,
+                                    uint64_t n_shards, uint64_t *d_global_nodes, tf21_stream_t stream) {
+    TF21_TRY(check_leaf_count(n_local_leafs));
+    TF21_TRY(check_leaf_count(n_shards));
+    if (shard >= n_shards || !d_local_nodes || !d_global_nodes) return TF21_E_BAD_ARG;
+    u64 total = (2 * n_local_leafs - 1) * 5;
+    TF21_LAUNCH(merkle_scatter_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, d_local_nodes,
+                n_local_leafs, shard, n_shards, d_global_nodes);
+    return 0;
+}
+
+int tf21_merkle_build(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out) {
+    TF21_TRY(check_leaf_count(n_leafs));
+    if (!leafs || !nodes_out) return TF21_E_BAD_ARG;
+    DevBuf bl, bn;
+    TF21_TRY(bl.alloc(5 * n_leafs));
+    TF21_TRY(bn.alloc(10 * n_leafs));
+    TF21_CUDA(cudaMemcpy(bl.p, leafs, 5 * n_leafs * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_merkle_build_dev(bl.p, n_leafs, bn.p, nullptr));
+    TF21_CUDA(cudaMemcpy(nodes_out, bn.p, 10 * n_leafs * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tf21_merkle_root(const uint64_t *leafs, uint64_t n_leafs, uint64_t root_out[5]) {
+    TF21_TRY(check_leaf_count(n_leafs));
+    if (!leafs || !root_out) return TF21_E_BAD_ARG;
+    DevBuf bl, br;
+    TF21_TRY(bl.alloc(5 * n_leafs));
+    TF21_TRY(br.alloc(5));
+    TF21_CUDA(cudaMemcpy(bl.p, leafs, 5 * n_leafs * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_merkle_root_dev(bl.p, n_leafs, br.p, nullptr));
+    TF21_CUDA(cudaMemcpy(root_out, br.p, 5 * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// tip5.cuh -- Tip5 permutation on raw Montgomery words, one hash per thread, state in registers.
+//
+// Replaces Tip5::permutation and its scalar/AVX-512 round functions
+// (twenty-first/src/tip5/mod.rs:175-253, 529-533; tip5/avx512.rs:13-175).
+// Per round (pinned by the reference KATs tip5/mod.rs:1145-1206,1294-1362):
+//   lanes 0..3 : byte-wise LOOKUP_TABLE on the little-endian bytes of the raw word  (:197-207)
+//   lanes 4..15: raw^7 mod p (valid on Montgomery words because R^6 = 1)            (:189-193)
+//   t = circulant(MDS_MATRIX_FIRST_COLUMN) * s mod p                                (:154-157, naive.rs:54-68)
+//   s = t + ROUND_CONSTANTS[16 r + i] * 2^64 mod p                                  (:68-149, 178-180)
+// The MDS step follows the accumulator idea of the reference's AVX-512 path (avx512.rs:124-175):
+// split every lane into 32-bit halves, accumulate 16-bit x 32-bit products in 64-bit registers
+// (bounded by 2^52), seed the accumulators with the round-constant halves, reduce once.
+#pragma once
+#include "field.cuh"
+
+#define TIP5_STATE 16
+#define TIP5_RATE 10
+#define TIP5_ROUNDS 5
+#define TIP5_DIGEST 5
+#define TIP5_RAW_ONE 0xFFFFFFFFull /* BFieldElement::ONE as a raw word = 2^64 mod p */
+
+// Filled by upload_tip5_constants (tip5_kernels.cuh): raw round constants split in 32-bit halves,
+// zero-extended to u64, and the S-box table.
+__constant__ u64 c_tip5_rc_lo[TIP5_ROUNDS * TIP5_STATE];
+__constant__ u64 c_tip5_rc_hi[TIP5_ROUNDS * TIP5_STATE];
+__constant__ uint8_t c_tip5_lut[256];
+
+// MDS_MATRIX_FIRST_COLUMN, tip5/mod.rs:154-157
+#define TIP5_MDS(k)                                                                              \
+    ((k) == 0 ? 61402u : (k) == 1 ? 1108u : (k) == 2 ? 28750u : (k) == 3 ? 33823u : (k) == 4 ? 7454u \
+     : (k) == 5 ? 43244u : (k) == 6 ? 53865u : (k) == 7 ? 12034u : (k) == 8 ? 56951u              \
+     : (k) == 9 ? 27521u : (k) == 10 ? 41351u : (k) == 11 ? 40901u : (k) == 12 ? 12021u           \
+     : (k) == 13 ? 59689u : (k) == 14 ? 26798u : 17845u)
+
+#ifdef __CUDACC__
+
+// copy the 256-byte S-box table into shared memory (call once per CTA, then __syncthreads)
+__device__ __forceinline__ void tip5_load_lut(uint8_t *s_lut) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = c_tip5_lut[i];
+}
+
+__device__ __forceinline__ u32 tip5_lut_word(u32 w, const uint8_t *s_lut) {
+    u32 b0 = s_lut[w & 0xff];
+    u32 b1 = s_lut[(w >> 8) & 0xff];
+    u32 b2 = s_lut[(w >> 16) & 0xff];
+    u32 b3 = s_lut[w >> 24];
+    return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+
+// s: 16 raw words as stored by the caller (the S-box LUT acts on the raw bytes as they are, like
+// split_and_lookup tip5/mod.rs:197-207; lanes 4..15 may be any representative mod p).
+// On exit lanes 0..3 are canonical, lanes 4..15 weak; callers canonicalise what they store.
+__device__ __forceinline__ void tip5_permutation(u64 (&s)[TIP5_STATE], const uint8_t *s_lut) {
+#pragma unroll 1
+    for (int r = 0; r < TIP5_ROUNDS; r++) {
+        // ---- S-box ----
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            u32 lo = tip5_lut_word((u32)s[i], s_lut);
+            u32 hi = tip5_lut_word((u32)(s[i] >> 32), s_lut);
+            s[i] = gl_pack(lo, hi);
+        }
+#pragma unroll
+        for (int i = 4; i < TIP5_STATE; i++) {
+            u64 x = s[i];
+            u64 x2 = gl_mul(x, x);
+            u64 x4 = gl_mul(x2, x2);
+            u64 x6 = gl_mul(x2, x4);
+            s[i] = gl_mul(x, x6);
+        }
+        // ---- MDS + round constants ----
+        u64 acc_lo[TIP5_STATE], acc_hi[TIP5_STATE];
+#pragma unroll
+        for (int i = 0; i < TIP5_STATE; i++) {
+            acc_lo[i] = c_tip5_rc_lo[r * TIP5_STATE + i];
+            acc_hi[i] = c_tip5_rc_hi[r * TIP5_STATE + i];
+        }
+#pragma unroll
+        for (int j = 0; j < TIP5_STATE; j++) {
+            u32 lo = (u32)s[j], hi = (u32)(s[j] >> 32);
+#pragma unroll
+            for (int i = 0; i < TIP5_STATE; i++) {
+                const u32 m = TIP5_MDS((i - j) & 15);
+                acc_lo[i] += (u64)lo * m;
+                acc_hi[i] += (u64)hi * m;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TIP5_STATE; i++) {
+            // value = acc_lo + acc_hi * 2^32, acc_* < 2^53
+            u64 x0 = acc_lo[i] + (acc_hi[i] << 32);
+            u32 x1 = (u32)(acc_hi[i] >> 32) + (x0 < acc_lo[i] ? 1u : 0u);
+            u64 v = gl_reduce96(x0, x1);
+            s[i] = (i < 4) ? gl_canon(v) : v;
+        }
+    }
+}
+
+#endif

@@ -1,0 +1,236 @@
+// tip5_kernels.cuh -- batched Tip5 kernels and the level-batched Merkle build (K3, K4 of SURVEY.md).
+//
+// Replaces Tip5::{permutation, hash_10, hash_pair, hash_varlen} (tip5/mod.rs:529-533, 559-586,
+// 617-623; sponge.rs:41-56) applied over a batch -- the caller-side `par_iter().map(Tip5::hash_10)`
+// pattern of benches/tip5.rs:43-49 -- and MerkleTree::{par_new, sequential_new, *_frugal_root}
+// (util_types/merkle_tree.rs:149-222, 299-364, 393-429).
+//
+// Data layout in HBM: digests are 5 consecutive u64 (40 B), a hash_10 input is 10 consecutive u64
+// (80 B, 16-byte aligned), a Merkle node array is heap indexed exactly like the reference's
+// `Vec<Digest>`: nodes[0] = 0, nodes[1] = root, nodes[n..2n) = leaves.  The children of the level
+// holding `cnt` nodes are the 10*cnt contiguous words at nodes + 10*cnt, so one level is one
+// hash_10 batch whose output is written at nodes + 5*cnt.
+#pragma once
+#include "runtime.cuh"
+#include "tip5.cuh"
+
+namespace tf21 {
+
+// ROUND_CONSTANTS, tip5/mod.rs:68-149 (canonical values; the kernel uses value * 2^64 mod p)
+static const u64 kTip5RoundConstants[TIP5_ROUNDS * TIP5_STATE] = {
+    13630775303355457758ull, 16896927574093233874ull, 10379449653650130495ull, 1965408364413093495ull,
+    15232538947090185111ull, 15892634398091747074ull, 3989134140024871768ull,  2851411912127730865ull,
+    8709136439293758776ull,  3694858669662939734ull,  12692440244315327141ull, 10722316166358076749ull,
+    12745429320441639448ull, 17932424223723990421ull, 7558102534867937463ull,  15551047435855531404ull,
+    17532528648579384106ull, 5216785850422679555ull,  15418071332095031847ull, 11921929762955146258ull,
+    9738718993677019874ull,  3464580399432997147ull,  13408434769117164050ull, 264428218649616431ull,
+    4436247869008081381ull,  4063129435850804221ull,  2865073155741120117ull,  5749834437609765994ull,
+    6804196764189408435ull,  17060469201292988508ull, 9475383556737206708ull,  12876344085611465020ull,
+    13835756199368269249ull, 1648753455944344172ull,  9836124473569258483ull,  12867641597107932229ull,
+    11254152636692960595ull, 16550832737139861108ull, 11861573970480733262ull, 1256660473588673495ull,
+    13879506000676455136ull, 10564103842682358721ull, 16142842524796397521ull, 3287098591948630584ull,
+    685911471061284805ull,   5285298776918878023ull,  18310953571768047354ull, 3142266350630002035ull,
+    549990724933663297ull,   4901984846118077401ull,  11458643033696775769ull, 8706785264119212710ull,
+    12521758138015724072ull, 11877914062416978196ull, 11333318251134523752ull, 3933899631278608623ull,
+    16635128972021157924ull, 10291337173108950450ull, 4142107155024199350ull,  16973934533787743537ull,
+    11068111539125175221ull, 17546769694830203606ull, 5315217744825068993ull,  4609594252909613081ull,
+    3350107164315270407ull,  17715942834299349177ull, 9600609149219873996ull,  12894357635820003949ull,
+    4597649658040514631ull,  7735563950920491847ull,  1663379455870887181ull,  13889298103638829706ull,
+    7375530351220884434ull,  3502022433285269151ull,  9231805330431056952ull,  9252272755288523725ull,
+    10014268662326746219ull, 15565031632950843234ull, 1209725273521819323ull,  6024642864597845108ull,
+};
+
+inline int upload_tip5_constants() {
+    u64 lo[TIP5_ROUNDS * TIP5_STATE], hi[TIP5_ROUNDS * TIP5_STATE];
+    for (int i = 0; i < TIP5_ROUNDS * TIP5_STATE; i++) {
+        u64 raw = hgl_to_raw(kTip5RoundConstants[i]);
+        lo[i] = raw & 0xffffffffull;
+        hi[i] = raw >> 32;
+    }
+    uint8_t lut[256];
+    // LOOKUP_TABLE, tip5/mod.rs:50-64 = ((x+1)^3 + 256) mod 257 (tip5/mod.rs:1022-1053)
+    for (unsigned i = 0; i < 256; i++) lut[i] = (uint8_t)(((i + 1) * (i + 1) * (i + 1) + 256) % 257);
+    TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc_lo, lo, sizeof(lo)));
+    TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc_hi, hi, sizeof(hi)));
+    TF21_CUDA(cudaMemcpyToSymbol(c_tip5_lut, lut, sizeof(lut)));
+    return 0;
+}
+
+constexpr int kTip5Threads = 128;
+
+// in-place permutation of `count` 16-word states (Tip5::permutation, tip5/mod.rs:529-533)
+__global__ void __launch_bounds__(kTip5Threads) tip5_permute_kernel(u64 *__restrict__ states, u64 count) {
+    __shared__ uint8_t s_lut[256];
+    tip5_load_lut(s_lut);
+    __syncthreads();
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 s[TIP5_STATE];
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(states + 16 * i);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        ulonglong2 v = src[k];
+        s[2 * k] = v.x;
+        s[2 * k + 1] = v.y;
+    }
+    tip5_permutation(s, s_lut);
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(states + 16 * i);
+#pragma unroll
+    for (int k = 0; k < 8; k++) dst[k] = make_ulonglong2(gl_canon(s[2 * k]), gl_canon(s[2 * k + 1]));
+}
+
+// Tip5::hash_10 / hash_pair over a batch (tip5/mod.rs:559-586): state = in[0..10) | ONE x 6
+__global__ void __launch_bounds__(kTip5Threads)
+    tip5_hash10_kernel(const u64 *__restrict__ in, u64 count, u64 *__restrict__ out) {
+    __shared__ uint8_t s_lut[256];
+    tip5_load_lut(s_lut);
+    __syncthreads();
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 s[TIP5_STATE];
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(in + 10 * i);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        ulonglong2 v = src[k];
+        s[2 * k] = v.x;
+        s[2 * k + 1] = v.y;
+    }
+#pragma unroll
+    for (int k = TIP5_RATE; k < TIP5_STATE; k++) s[k] = TIP5_RAW_ONE;
+    tip5_permutation(s, s_lut);
+    u64 *dst = out + 5 * i;
+#pragma unroll
+    for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
+}
+
+// Top of a Merkle tree in one CTA: levels with cnt = first_cnt, first_cnt/2, ..., 1.
+// nodes: heap-indexed array; the children level (2*first_cnt nodes) is already complete.
+constexpr int kMerkleTailThreads = 256;
+__global__ void __launch_bounds__(kMerkleTailThreads) merkle_tail_kernel(u64 *nodes, u32 first_cnt) {
+    __shared__ uint8_t s_lut[256];
+    tip5_load_lut(s_lut);
+    __syncthreads();
+    for (u32 cnt = first_cnt; cnt >= 1; cnt >>= 1) {
+        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) {
+            u64 s[TIP5_STATE];
+            const u64 *src = nodes + 10ull * (cnt + i);
+#pragma unroll
+            for (int k = 0; k < TIP5_RATE; k++) s[k] = src[k];
+#pragma unroll
+            for (int k = TIP5_RATE; k < TIP5_STATE; k++) s[k] = TIP5_RAW_ONE;
+            tip5_permutation(s, s_lut);
+            u64 *dst = nodes + 5ull * (cnt + i);
+#pragma unroll
+            for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+// Tip5::hash_varlen over rows (tip5/mod.rs:617-623, sponge.rs:41-56): one row per thread,
+// overwrite-mode absorb of 10-word chunks, padding 1,0,.. always present.
+__global__ void __launch_bounds__(kTip5Threads)
+    tip5_hash_rows_kernel(const u64 *__restrict__ rows, u64 row_len, u64 n_rows, u64 *__restrict__ out) {
+    __shared__ uint8_t s_lut[256];
+    tip5_load_lut(s_lut);
+    __syncthreads();
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const u64 *row = rows + i * row_len;
+    u64 s[TIP5_STATE];
+#pragma unroll
+    for (int k = 0; k < TIP5_STATE; k++) s[k] = 0;
+    u64 full = row_len / TIP5_RATE;
+    for (u64 c = 0; c < full; c++) {
+#pragma unroll
+        for (int k = 0; k < TIP5_RATE; k++) s[k] = row[c * TIP5_RATE + k];
+        tip5_permutation(s, s_lut);
+    }
+    u32 rem = (u32)(row_len - full * TIP5_RATE);
+#pragma unroll
+    for (int k = 0; k < TIP5_RATE; k++) {
+        u64 v = 0;
+        if ((u32)k < rem) v = row[full * TIP5_RATE + k];
+        if ((u32)k == rem) v = TIP5_RAW_ONE;
+        s[k] = v;
+    }
+    tip5_permutation(s, s_lut);
+    u64 *dst = out + 5 * i;
+#pragma unroll
+    for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
+}
+
+// nodes[0] = 0 and nodes[n..2n) = leafs  (initialize_merkle_tree_nodes, merkle_tree.rs:393-429)
+__global__ void merkle_init_kernel(const u64 *__restrict__ leafs, u64 n_leaf_words, u64 *__restrict__ nodes) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    if (i < 5) nodes[i] = 0;
+    for (; i < n_leaf_words; i += stride) nodes[n_leaf_words + i] = leafs[i];
+}
+
+// local subtree -> global heap positions (see tf21_merkle_scatter_subtree_dev)
+__global__ void merkle_scatter_kernel(const u64 *__restrict__ local, u64 n_local, u64 shard, u64 n_shards,
+                                      u64 *__restrict__ global) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // word index into local nodes, from node 1
+    u64 total = (2 * n_local - 1) * 5;
+    if (t >= total) return;
+    u64 node = 1 + t / 5, lane = t % 5;
+    unsigned level = 63u - (unsigned)__clzll((long long)node);  // node in [2^level, 2^(level+1))
+    u64 width = 1ull << level;
+    u64 g = n_shards * width + shard * width + (node - width);
+    global[5 * g + lane] = local[5 * node + lane];
+}
+
+inline unsigned grid_for(u64 count, int threads) { return (unsigned)((count + threads - 1) / threads); }
+
+inline int launch_permute(u64 *d_states, u64 count, cudaStream_t st) {
+    if (count == 0) return 0;
+    TF21_LAUNCH(tip5_permute_kernel, grid_for(count, kTip5Threads), kTip5Threads, 0, st, d_states, count);
+    return 0;
+}
+
+inline int launch_hash10(const u64 *d_in, u64 count, u64 *d_out, cudaStream_t st) {
+    if (count == 0) return 0;
+    TF21_LAUNCH(tip5_hash10_kernel, grid_for(count, kTip5Threads), kTip5Threads, 0, st, d_in, count, d_out);
+    return 0;
+}
+
+inline int launch_hash_rows(const u64 *d_rows, u64 row_len, u64 n_rows, u64 *d_out, cudaStream_t st) {
+    if (n_rows == 0) return 0;
+    TF21_LAUNCH(tip5_hash_rows_kernel, grid_for(n_rows, kTip5Threads), kTip5Threads, 0, st, d_rows, row_len,
+                n_rows, d_out);
+    return 0;
+}
+
+constexpr u32 kMerkleTailCnt = 256;  // levels with <= this many nodes are finished by one CTA
+
+// fills nodes[1..n) given nodes[n..2n) (sequentially_fill_tree, merkle_tree.rs:216-222, level-batched)
+inline int launch_merkle_levels(u64 *d_nodes, u64 n_leafs, cudaStream_t st) {
+    u64 cnt = n_leafs / 2;
+    while (cnt > kMerkleTailCnt) {
+        TF21_TRY(launch_hash10(d_nodes + 10 * cnt, cnt, d_nodes + 5 * cnt, st));
+        cnt >>= 1;
+    }
+    if (cnt >= 1) {
+        TF21_LAUNCH(merkle_tail_kernel, 1, kMerkleTailThreads, 0, st, d_nodes, (u32)cnt);
+    }
+    return 0;
+}
+
+inline int check_leaf_count(u64 n) {
+    if (n == 0) return TF21_E_TOO_FEW_LEAFS;                    // merkle_tree.rs:394-396
+    if (n & (n - 1)) return TF21_E_INCORRECT_NUMBER_OF_LEAFS;   // merkle_tree.rs:398-401
+    if (n > (1ull << 40)) return TF21_E_ALLOC;                  // TreeTooHigh analogue
+    return 0;
+}
+
+inline int merkle_build_dev(const u64 *d_leafs, u64 n, u64 *d_nodes, cudaStream_t st) {
+    TF21_TRY(check_leaf_count(n));
+    u64 words = 5 * n;
+    unsigned grid = (unsigned)std::min<u64>((words + 255) / 256, 148 * 16);
+    TF21_LAUNCH(merkle_init_kernel, grid, 256, 0, st, d_leafs, words, d_nodes);
+    return launch_merkle_levels(d_nodes, n, st);
+}
+
+}  // namespace tf21

@@ -1,0 +1,71 @@
+"""Device-resident entry points: the measured path.  Buffers are torch CUDA tensors of dtype int64
+(bit patterns of the raw u64 words); torch is only used for device memory and streams."""
+from __future__ import annotations
+
+import torch
+
+from . import _binding as B
+
+
+def _p(t: torch.Tensor):
+    assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()
+    return t.data_ptr() if t.numel() else None
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def init(device: int) -> None:
+    B.check(B.lib.tf21_init(device))
+
+
+def ntt_(data: torch.Tensor, n: int, width: int = 1, inverse: bool = False) -> None:
+    batch = data.numel() // (n * width) if n else 0
+    B.check(B.lib.tf21_ntt_dev(_p(data), n, width, batch, int(inverse), _stream()))
+
+
+def coset_evaluate(coeffs: torch.Tensor, width: int, offset_raw: int, order: int, out: torch.Tensor) -> None:
+    B.check(B.lib.tf21_coset_evaluate_dev(_p(coeffs), coeffs.numel() // width, width, offset_raw, order, _p(out),
+                                          _stream()))
+
+
+def coset_interpolate(values: torch.Tensor, width: int, offset_raw: int, out: torch.Tensor) -> None:
+    B.check(B.lib.tf21_coset_interpolate_dev(_p(values), values.numel() // width, width, offset_raw, _p(out),
+                                             _stream()))
+
+
+def coset_lde(values: torch.Tensor, width: int, offset_in_raw: int, n_out: int, offset_out_raw: int,
+              out: torch.Tensor) -> None:
+    B.check(B.lib.tf21_coset_lde_dev(_p(values), values.numel() // width, offset_in_raw, n_out, offset_out_raw,
+                                     width, _p(out), _stream()))
+
+
+def tip5_permute_(states: torch.Tensor) -> None:
+    B.check(B.lib.tf21_tip5_permute_dev(_p(states), states.numel() // 16, _stream()))
+
+
+def tip5_hash_10(inp: torch.Tensor, out: torch.Tensor) -> None:
+    B.check(B.lib.tf21_tip5_hash_10_dev(_p(inp), inp.numel() // 10, _p(out), _stream()))
+
+
+def tip5_hash_rows(rows: torch.Tensor, row_len: int, out: torch.Tensor) -> None:
+    n_rows = rows.numel() // row_len if row_len else out.numel() // 5
+    B.check(B.lib.tf21_tip5_hash_rows_dev(_p(rows), row_len, n_rows, _p(out), _stream()))
+
+
+def merkle_build(leafs: torch.Tensor, nodes: torch.Tensor) -> None:
+    B.check(B.lib.tf21_merkle_build_dev(_p(leafs), leafs.numel() // 5, _p(nodes), _stream()))
+
+
+def merkle_root(leafs: torch.Tensor, root: torch.Tensor) -> None:
+    B.check(B.lib.tf21_merkle_root_dev(_p(leafs), leafs.numel() // 5, _p(root), _stream()))
+
+
+def merkle_scatter_subtree(local_nodes: torch.Tensor, shard: int, n_shards: int, global_nodes: torch.Tensor) -> None:
+    B.check(B.lib.tf21_merkle_scatter_subtree_dev(_p(local_nodes), local_nodes.numel() // 10, shard, n_shards,
+                                                  _p(global_nodes), _stream()))
+
+
+def kernel_launch_count() -> int:
+    return int(B.lib.tf21_kernel_launch_count())
