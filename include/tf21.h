@@ -62,6 +62,12 @@ int tf21_memcpy_h2d(void *dst_dev, const void *src_host, uint64_t bytes, tf21_st
 int tf21_memcpy_d2h(void *dst_host, const void *src_dev, uint64_t bytes, tf21_stream_t stream);
 int tf21_stream_sync(tf21_stream_t stream);
 
+/* Diagnostic: element-wise device field arithmetic on raw words (used by the parity tests to pin
+ * the Goldilocks primitives): op 0 add, 1 sub, 2 mul (all mod p, canonical result), 3 canonicalise,
+ * 4 weak add then canonicalise, 5 reduce a 96-bit value a + (b & 0xffffffff) * 2^64.             */
+int tf21_selftest_field_dev(int op, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out,
+                            uint64_t n, tf21_stream_t stream);
+
 /* ---- NTT: math::ntt::ntt / intt (ntt.rs:67-82, 109-125) ------------------------------------- */
 /* In place over `batch` contiguous arrays of n*width words. n == 0 or 1 is a no-op.
  * out[i] = sum_j x[j] * omega_n^(i j), natural order in and out; intt also multiplies by n^-1.  */

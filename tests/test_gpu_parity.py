@@ -40,6 +40,51 @@ def adversarial(n, w=1):
     return sets
 
 
+# ---- field primitives -------------------------------------------------------------------------------
+def test_device_field_primitives(tf):
+    import torch
+
+    cuda = torch.device("cuda:0")
+    edge = [0, 1, 2, 0xFFFFFFFF, 0x100000000, 0xFFFFFFFF00000000, P - 1, P - 2, P - 0xFFFFFFFF, 1 << 63,
+            0x3FFFFFFFC, (1 << 32) - 2]
+    a_list, b_list = [], []
+    for x in edge:
+        for y in edge:
+            a_list.append(x)
+            b_list.append(y)
+    ra, rb = rnd(11, 20000), rnd(12, 20000)
+    a = np.concatenate([np.array(a_list, dtype=np.uint64), ra])
+    b = np.concatenate([np.array(b_list, dtype=np.uint64), rb])
+    da = torch.from_numpy(a.view(np.int64)).to(cuda)
+    db = torch.from_numpy(b.view(np.int64)).to(cuda)
+    out = torch.zeros_like(da)
+
+    def run(op, xa=da, xb=db):
+        tf.check(tf.lib.tf21_selftest_field_dev(op, xa.data_ptr(), xb.data_ptr(), out.data_ptr(), xa.numel(), None))
+        torch.cuda.synchronize()
+        return [int(v) for v in out.cpu().numpy().view(np.uint64)]
+
+    ai, bi = [int(v) for v in a], [int(v) for v in b]
+    assert run(0) == [(x + y) % P for x, y in zip(ai, bi)]
+    assert run(1) == [(x - y) % P for x, y in zip(ai, bi)]
+    assert run(2) == [(x * y) % P for x, y in zip(ai, bi)]
+    # arbitrary (non-canonical) u64 operands for mul / canon / weak add / reduce96
+    wa = np.concatenate([np.array([(1 << 64) - 1, (1 << 64) - 2, P, P + 1, (1 << 64) - (1 << 32)], dtype=np.uint64),
+                         np.random.default_rng(5).integers(0, 1 << 64, 20000, dtype=np.uint64)])
+    wb = np.random.default_rng(6).integers(0, 1 << 64, wa.size, dtype=np.uint64)
+    wb[:5] = np.array([(1 << 64) - 1, P, 3, (1 << 64) - 1, (1 << 64) - (1 << 32)], dtype=np.uint64)
+    dwa = torch.from_numpy(wa.view(np.int64)).to(cuda)
+    dwb = torch.from_numpy(wb.view(np.int64)).to(cuda)
+    out = torch.zeros_like(dwa)
+    wai, wbi = [int(v) for v in wa], [int(v) for v in wb]
+    assert run(2, dwa, dwb) == [(x * y) % P for x, y in zip(wai, wbi)]
+    assert run(3, dwa, dwb) == [x % P for x in wai]
+    wbc = np.array([v % P for v in wbi], dtype=np.uint64)
+    dwbc = torch.from_numpy(wbc.view(np.int64)).to(cuda)
+    assert run(4, dwa, dwbc) == [(x + int(y)) % P for x, y in zip(wai, wbc)]
+    assert run(5, dwa, dwb) == [(x + ((y & 0xFFFFFFFF) << 64)) % P for x, y in zip(wai, wbi)]
+
+
 # ---- NTT --------------------------------------------------------------------------------------------
 def test_ntt_reference_kats(tf, oracle, kats):
     for name in ("bfield_basic", "bfield_max", "bfield_len32"):

@@ -24,34 +24,37 @@ typedef uint32_t u32;
 
 __device__ __forceinline__ u64 gl_pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
 
-// [0, 2^64) -> [0, p).  a >= p  <=>  a + EPS carries out of 64 bits, and then a - p = a + EPS mod 2^64.
+// [0, 2^64) -> [0, p):  t = a - p borrows  <=>  a < p.  Only borrow-type flags are used: a `subc`
+// that consumes the carry of an `add.cc` does NOT yield -carry (measured on sm_100a), so carry
+// and borrow chains are never mixed in this file.
 __device__ __forceinline__ u64 gl_canon(u64 a) {
     u32 lo, hi, m;
     asm("{\n\t"
         ".reg .u32 l2, h2;\n\t"
-        "add.cc.u32 l2,%3,0xffffffff;\n\t"
-        "addc.cc.u32 h2,%4,0;\n\t"
-        "subc.u32 %2,0,0;\n\t" /* m = carry ? 0xffffffff : 0 */
-        "lop3.b32 %0,%3,l2,%2,0xD8;\n\t" /* m ? l2 : lo */
-        "lop3.b32 %1,%4,h2,%2,0xD8;\n\t"
+        "sub.cc.u32 l2,%3,1;\n\t"
+        "subc.cc.u32 h2,%4,0xffffffff;\n\t"
+        "subc.u32 %2,0,0;\n\t" /* m = (a < p) ? 0xffffffff : 0 */
+        "lop3.b32 %0,l2,%3,%2,0xD8;\n\t" /* m ? lo : l2 */
+        "lop3.b32 %1,h2,%4,%2,0xD8;\n\t"
         "}"
-        : "=r"(lo), "=r"(hi), "=r"(m)
+        : "=&r"(lo), "=&r"(hi), "=&r"(m)
         : "r"((u32)a), "r"((u32)(a >> 32)));
     return gl_pack(lo, hi);
 }
 
 // weak add: a, b any u64 with a + b < 2^64 + p (e.g. one of them canonical) -> any u64.
-// One wrap correction: 2^64 = EPS (mod p).
+// One wrap correction: 2^64 = EPS (mod p); c*EPS is added as (c << 32) - c, which cannot wrap again.
 __device__ __forceinline__ u64 gl_add_weak(u64 a, u64 b) {
     u32 lo, hi, m;
     asm("{\n\t"
         "add.cc.u32 %0,%3,%5;\n\t"
         "addc.cc.u32 %1,%4,%6;\n\t"
-        "subc.u32 %2,0,0;\n\t" /* m = carry ? 0xffffffff : 0 */
-        "add.cc.u32 %0,%0,%2;\n\t"
-        "addc.u32 %1,%1,0;\n\t"
+        "addc.u32 %2,0,0;\n\t" /* c = carry (0/1);  r += c * EPS = (c << 32) - c */
+        "sub.cc.u32 %0,%0,%2;\n\t"
+        "subc.u32 %1,%1,0;\n\t"
+        "add.u32 %1,%1,%2;\n\t"
         "}"
-        : "=r"(lo), "=r"(hi), "=r"(m)
+        : "=&r"(lo), "=&r"(hi), "=&r"(m)
         : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
     return gl_pack(lo, hi);
 }
@@ -66,7 +69,7 @@ __device__ __forceinline__ u64 gl_sub(u64 a, u64 b) {
         "sub.cc.u32 %0,%0,%2;\n\t"
         "subc.u32 %1,%1,0;\n\t"
         "}"
-        : "=r"(lo), "=r"(hi), "=r"(m)
+        : "=&r"(lo), "=&r"(hi), "=&r"(m)
         : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
     return gl_pack(lo, hi);
 }
@@ -106,9 +109,10 @@ __device__ __forceinline__ u64 gl_reduce128(u32 r0, u32 r1, u32 r2, u32 r3) {
         "subc.u32    %1, %1, 0;\n\t"
         "mad.lo.cc.u32  %0, %5, 0xffffffff, %0;\n\t"
         "madc.hi.cc.u32 %1, %5, 0xffffffff, %1;\n\t"
-        "subc.u32    %2, 0, 0;\n\t"
-        "add.cc.u32  %0, %0, %2;\n\t"
-        "addc.u32    %1, %1, 0;\n\t"
+        "addc.u32    %2, 0, 0;\n\t" /* c = carry;  r += c * EPS = (c << 32) - c */
+        "sub.cc.u32  %0, %0, %2;\n\t"
+        "subc.u32    %1, %1, 0;\n\t"
+        "add.u32     %1, %1, %2;\n\t"
         "}"
         : "=&r"(lo), "=&r"(hi), "=&r"(m)
         : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
@@ -131,9 +135,10 @@ __device__ __forceinline__ u64 gl_reduce96(u64 x0, u32 x1) {
     asm("{\n\t"
         "mad.lo.cc.u32  %0, %5, 0xffffffff, %3;\n\t"
         "madc.hi.cc.u32 %1, %5, 0xffffffff, %4;\n\t"
-        "subc.u32    %2, 0, 0;\n\t"
-        "add.cc.u32  %0, %0, %2;\n\t"
-        "addc.u32    %1, %1, 0;\n\t"
+        "addc.u32    %2, 0, 0;\n\t"
+        "sub.cc.u32  %0, %0, %2;\n\t"
+        "subc.u32    %1, %1, 0;\n\t"
+        "add.u32     %1, %1, %2;\n\t"
         "}"
         : "=&r"(lo), "=&r"(hi), "=&r"(m)
         : "r"((u32)x0), "r"((u32)(x0 >> 32)), "r"(x1));

@@ -167,6 +167,29 @@ int tf21_stream_sync(tf21_stream_t stream) {
     return 0;
 }
 
+// ---- diagnostics -----------------------------------------------------------------------------------
+__global__ void selftest_field_kernel(int op, const u64 *a, const u64 *b, u64 *out, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 x = a[i], y = b[i], r = 0;
+    switch (op) {
+        case 0: r = gl_add(x, y); break;        // canonical operands
+        case 1: r = gl_sub(x, y); break;        // canonical operands
+        case 2: r = gl_mulc(x, y); break;       // any operands
+        case 3: r = gl_canon(x); break;
+        case 4: r = gl_canon(gl_add_weak(x, y)); break;  // x any, y canonical
+        case 5: r = gl_canon(gl_reduce96(x, (u32)y)); break;
+    }
+    out[i] = r;
+}
+
+int tf21_selftest_field_dev(int op, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, uint64_t n,
+                            tf21_stream_t stream) {
+    if (n == 0) return 0;
+    TF21_LAUNCH(selftest_field_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, op, d_a, d_b, d_out, n);
+    return 0;
+}
+
 // ---- NTT -------------------------------------------------------------------------------------------
 int tf21_ntt_dev(uint64_t *d_data, uint64_t n, uint32_t width, uint64_t batch, int inverse, tf21_stream_t stream) {
     TF21_TRY(check_ntt_len(n, width));
