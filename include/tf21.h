@@ -55,6 +55,11 @@ const char *tf21_strerror(int code);
 const char *tf21_last_cuda_error(void);
 /* Number of kernels launched by this library in this process since start (bench bookkeeping).  */
 uint64_t tf21_kernel_launch_count(void);
+/* Per-launch device timing for roofline reporting: when enabled every kernel launch is bracketed
+ * by CUDA events on its stream.  tf21_profile_read writes "kernel_name milliseconds\n" per
+ * launch (launch order) and returns the buffer size needed; enable(0/1) also clears the log.   */
+int tf21_profile_enable(int on);
+int64_t tf21_profile_read(char *buf, uint64_t buflen);
 /* Stream-ordered device memory helpers so a host language needs no CUDA binding of its own.   */
 int tf21_malloc(void **dptr, uint64_t bytes);
 int tf21_free(void *dptr);

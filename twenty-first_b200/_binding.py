@@ -32,6 +32,8 @@ SIGNATURES = {
     "tf21_strerror": (ctypes.c_char_p, [i32]),
     "tf21_last_cuda_error": (ctypes.c_char_p, []),
     "tf21_kernel_launch_count": (u64, []),
+    "tf21_profile_enable": (i32, [i32]),
+    "tf21_profile_read": (ctypes.c_int64, [ctypes.c_char_p, u64]),
     "tf21_malloc": (i32, [ctypes.POINTER(vp), u64]),
     "tf21_free": (i32, [vp]),
     "tf21_memcpy_h2d": (i32, [vp, vp, u64, vp]),

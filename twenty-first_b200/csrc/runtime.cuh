@@ -41,10 +41,37 @@ inline int cuda_fail(cudaError_t e, const char *what, int line) {
         if (_rc != 0) return _rc; \
     } while (0)
 
+// Optional per-launch timing (tf21_profile_enable): CUDA events recorded on the launching stream
+// around every kernel, read back by tf21_profile_read.  Off by default; bench.py turns it on for
+// its roofline pass only.
+struct ProfRec {
+    const char *name;
+    cudaEvent_t a, b;
+};
+static std::atomic<bool> g_prof_enabled{false};
+static std::mutex g_prof_mutex;
+static std::vector<ProfRec> g_prof;
+
+inline void prof_begin(const char *name, cudaStream_t st, ProfRec *r) {
+    r->name = name;
+    cudaEventCreate(&r->a);
+    cudaEventCreate(&r->b);
+    cudaEventRecord(r->a, st);
+}
+inline void prof_end(cudaStream_t st, ProfRec *r) {
+    cudaEventRecord(r->b, st);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof.push_back(*r);
+}
+
 // every kernel launch of the library goes through this so bench.py can report gpu_launches
 #define TF21_LAUNCH(kernel, grid, block, smem, stream, ...)                     \
     do {                                                                        \
+        tf21::ProfRec _pr;                                                      \
+        const bool _prof = tf21::g_prof_enabled.load(std::memory_order_relaxed); \
+        if (_prof) tf21::prof_begin(#kernel, (stream), &_pr);                   \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
+        if (_prof) tf21::prof_end((stream), &_pr);                              \
         tf21::g_launches.fetch_add(1, std::memory_order_relaxed);               \
         cudaError_t _e = cudaGetLastError();                                    \
         if (_e != cudaSuccess) return tf21::cuda_fail(_e, #kernel, __LINE__);   \

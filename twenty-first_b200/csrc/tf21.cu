@@ -146,6 +146,38 @@ const char *tf21_strerror(int code) {
 const char *tf21_last_cuda_error(void) { return g_last_cuda_error; }
 uint64_t tf21_kernel_launch_count(void) { return g_launches.load(); }
 
+int tf21_profile_enable(int on) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    for (auto &r : g_prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    g_prof_enabled.store(on != 0);
+    return 0;
+}
+
+// writes "kernel_name milliseconds\n" per recorded launch, in launch order; returns the number of
+// bytes needed (call again with a larger buffer if it exceeds buflen)
+int64_t tf21_profile_read(char *buf, uint64_t buflen) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    std::string out;
+    for (auto &r : g_prof) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) return TF21_E_CUDA;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) return TF21_E_CUDA;
+        char line[160];
+        snprintf(line, sizeof(line), "%s %.6f\n", r.name, ms);
+        out += line;
+    }
+    if (buf && buflen) {
+        size_t ncopy = out.size() < buflen - 1 ? out.size() : buflen - 1;
+        memcpy(buf, out.data(), ncopy);
+        buf[ncopy] = 0;
+    }
+    return (int64_t)out.size() + 1;
+}
+
 int tf21_malloc(void **dptr, uint64_t bytes) {
     TF21_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
     return 0;

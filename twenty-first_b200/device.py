@@ -69,3 +69,25 @@ def merkle_scatter_subtree(local_nodes: torch.Tensor, shard: int, n_shards: int,
 
 def kernel_launch_count() -> int:
     return int(B.lib.tf21_kernel_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    B.check(B.lib.tf21_profile_enable(int(on)))
+
+
+def profile_read():
+    """[(kernel_name, ms), ...] in launch order"""
+    import ctypes
+
+    need = B.lib.tf21_profile_read(None, 0)
+    if need < 0:
+        B.check(int(need))
+    buf = ctypes.create_string_buffer(int(need) + 16)
+    got = B.lib.tf21_profile_read(buf, len(buf))
+    if got < 0:
+        B.check(int(got))
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, ms = line.rsplit(" ", 1)
+        out.append((name, float(ms)))
+    return out
