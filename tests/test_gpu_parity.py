@@ -83,6 +83,15 @@ def test_device_field_primitives(tf):
     dwbc = torch.from_numpy(wbc.view(np.int64)).to(cuda)
     assert run(4, dwa, dwbc) == [(x + int(y)) % P for x, y in zip(wai, wbc)]
     assert run(5, dwa, dwb) == [(x + ((y & 0xFFFFFFFF) << 64)) % P for x, y in zip(wai, wbi)]
+    # second-generation lazy primitives (any u64 first operand; second operand <= p)
+    wbp = wbc.copy()
+    wbp[:3] = np.array([P, P - 1, 0], dtype=np.uint64)  # t = p itself is allowed by gl_addl
+    dwbp = torch.from_numpy(wbp.view(np.int64)).to(cuda)
+    assert run(6, dwa, dwbp) == [(x + int(y)) % P for x, y in zip(wai, wbp)]
+    assert run(7, dwa, dwb) == [x % P for x in wai]
+    assert run(8, dwa, dwbc) == [(x - int(y)) % P for x, y in zip(wai, wbc)]
+    for s in list(range(3, 96, 3)) + [1, 31, 65, 95]:
+        assert run(100 + s, dwa, dwb) == [(x << s) % P for x in wai], f"shift {s}"
 
 
 # ---- NTT --------------------------------------------------------------------------------------------

@@ -145,6 +145,98 @@ __device__ __forceinline__ u64 gl_reduce96(u64 x0, u32 x1) {
     return gl_pack(lo, hi);
 }
 
+// x * 2^S mod p for a compile-time (after unrolling) 0 <= S < 96; x < p -> result < p.
+// Every root of unity of order <= 64 is a power of two (omega_64 = 2^39, b_field_element.rs:43-78),
+// so the butterflies of a 32-point sub-transform need no 64x64 multiply: shift, then fold with
+// 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32 (mod p).
+__device__ __forceinline__ u64 gl_mul_pow2(u64 x, const int S) {
+    if (S == 0) return x;
+    const int q = S >> 5, t = S & 31;
+    const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
+    u32 y0, y1, y2;
+    if (t == 0) {
+        y0 = x0;
+        y1 = x1;
+        y2 = 0;
+    } else {
+        y0 = x0 << t;
+        y1 = __funnelshift_l(x0, x1, t);
+        y2 = x1 >> (32 - t);
+    }
+    if (q == 0) {  // y0 + y1 2^32 + y2 2^64
+        return gl_canon(gl_reduce96(gl_pack(y0, y1), y2));
+    } else if (q == 1) {  // y0 2^32 + y1 2^64 + y2 2^96 = (y0 << 32) + y1 EPS - y2
+        u64 a = (u64)y1 * GL_EPS;  // <= (2^32-1)^2 < p
+        if (t != 0) a = gl_sub(a, (u64)y2);
+        return gl_add(a, (u64)y0 << 32);  // (y0 << 32) <= p - 1
+    } else {  // y0 2^64 + y1 2^96 + y2 2^128 = y0 EPS - (y1 + y2 2^32)
+        u64 a = (u64)y0 * GL_EPS;
+        return gl_sub(a, gl_pack(y1, y2));  // y2 < 2^31 => operand < p
+    }
+}
+
+// ---- second-generation primitives: integer ALU / FMA-pipe balanced ---------------------------------
+// Measured on B200 (tools/ubench.cu): IADD3/LOP3/SHF/SEL/ISETP issue at one warp instruction per
+// 2 cycles per SM sub-partition on the ALU pipe; IMAD (32-bit) the same on the FMA pipe;
+// IMAD.WIDE / IMAD.HI one per 5.3 cycles on the FMA pipe; both pipes run concurrently.  The
+// butterfly-heavy kernels are ALU bound, so the wrap corrections below are expressed as one
+// IMAD.WIDE (c * EPS + s) instead of two or three ALU instructions.
+
+// s + c * EPS (mod 2^64), c in {0,1}.  Compiles to a single IMAD.WIDE.U32.
+__device__ __forceinline__ u64 gl_fix(u64 s, u32 c) { return s + (u64)c * GL_EPS; }
+
+// lazy add: a any u64, t <= p  ->  any u64 (value a + t mod p).  3 ALU + 1 IMAD.WIDE.
+__device__ __forceinline__ u64 gl_addl(u64 a, u64 t) {
+    u32 lo, hi, c;
+    asm("add.cc.u32 %0,%3,%5;\n\taddc.cc.u32 %1,%4,%6;\n\taddc.u32 %2,0,0;"
+        : "=r"(lo), "=r"(hi), "=r"(c)
+        : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)t), "r"((u32)(t >> 32)));
+    return gl_fix(gl_pack(lo, hi), c);
+}
+
+// any u64 -> [0, p):  x >= p  <=>  hi == 0xffffffff && lo != 0.  2 ISETP + SEL + 1 IMAD.WIDE.
+__device__ __forceinline__ u64 gl_canonw(u64 x) {
+    u32 f;
+    asm("{\n\t.reg .pred p1, p2;\n\t"
+        "setp.eq.u32 p1, %2, 0xffffffff;\n\t"
+        "setp.ne.and.u32 p2, %1, 0, p1;\n\t"
+        "selp.u32 %0, 1, 0, p2;\n\t}"
+        : "=r"(f)
+        : "r"((u32)x), "r"((u32)(x >> 32)));
+    return gl_fix(x, f);
+}
+
+// x * 2^S mod p with a CANONICAL result; x any u64; compile-time 0 < S < 96 with S % 32 != 0
+// (every shift twiddle of a 32- or 64-point transform: S is a multiple of 3).
+// z = x << (S % 32) as three 32-bit limbs, then fold by 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32.
+__device__ __forceinline__ u64 gl_shlc(u64 x, const int S) {
+    const int q = S >> 5, t = S & 31;
+    const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
+    const u32 z0 = x0 << t;
+    const u32 z1 = __funnelshift_l(x0, x1, t);
+    const u32 z2 = x1 >> (32 - t);  // < 2^31
+    if (q == 0) {
+        // (z1:z0) + z2 * EPS, z2 * EPS < 2^63: at most one wrap; carry and "r >= p" are exclusive
+        u32 lo, hi, c;
+        asm("mad.lo.cc.u32 %0,%5,0xffffffff,%3;\n\tmadc.hi.cc.u32 %1,%5,0xffffffff,%4;\n\taddc.u32 %2,0,0;"
+            : "=r"(lo), "=r"(hi), "=r"(c)
+            : "r"(z0), "r"(z1), "r"(z2));
+        const u32 f = c | ((hi == 0xffffffffu && lo != 0) ? 1u : 0u);
+        return gl_fix(gl_pack(lo, hi), f);
+    } else if (q == 1) {
+        // z * 2^32 = (z0 + z1) 2^32 - (z1 + z2):  T1 = (s : -carry) < p,  T2 = z1 + z2 < 2^33
+        const u32 s = z0 + z1;
+        const u32 c = (s < z0) ? 1u : 0u;
+        const u64 T1 = gl_pack(0u - c, s);
+        const u64 T2 = (u64)z1 + (u64)z2;
+        return gl_sub(T1, T2);
+    } else {
+        // z * 2^64 = z0 * EPS - (z2:z1):  z0 * EPS <= (2^32-1)^2 < p, (z2:z1) < 2^63
+        const u64 a = (u64)z0 * GL_EPS;
+        return gl_sub(a, gl_pack(z1, z2));
+    }
+}
+
 #endif  // __CUDACC__
 
 // ---- host-side helpers (table construction only) -----------------------------------------------

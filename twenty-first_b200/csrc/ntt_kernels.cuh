@@ -235,113 +235,4 @@ inline NttPlan make_plan(u32 log_n) {
     return p;
 }
 
-// Core entry: dst[b] = scale_post( NTT_n( zero_extend( scale_pre( src[b][0..n_in) ) ) ) ) for b < batch.
-// src arrays are n_in*w words apart, dst arrays n*w words apart.  src == dst is allowed when
-// n_in == n.  `scratch` (n*w*batch words) is required when log2 n > 10.
-inline int ntt_run(DeviceTables &tabs, const u64 *src, u64 n_in, u64 *dst, u64 n, u32 w, u64 batch, int inverse,
-                   ScaleTab pre, ScaleTab post, u64 post_scalar, u64 *scratch, cudaStream_t st) {
-    const u32 log_n = ilog2_u64(n);
-    const NttPlan plan = make_plan(log_n);
-    const u64 array_words = n * w;
-    const u64 src_array_words = n_in * w;
-    const u64 *tw_small = tabs.tw_small[inverse ? 1 : 0];
-
-    const u64 *cur_src = src;
-    u64 cur_src_words = src_array_words;
-    u64 cur_n_in = n_in;
-    ScaleTab cur_pre = pre;
-    u32 consumed = 0;  // log2 of N_1..N_{p-1}
-    for (u32 p = 0; p + 1 < plan.k; p++) {
-        ColPassArgs a{};
-        a.src = cur_src;
-        a.dst = scratch;
-        a.src_array_words = cur_src_words;
-        a.dst_array_words = array_words;
-        a.log_np = plan.l[p];
-        a.w = w;
-        const u32 log_inner = log_n - consumed - plan.l[p];
-        a.inner_words = ((u64)1 << log_inner) * w;
-        a.n_col_tiles = (u32)((a.inner_words + kNttColTile - 1) / kNttColTile);
-        a.n_outer = 1u << consumed;
-        a.n_in_elems = cur_n_in;
-        a.tw_np = tw_small + ((1u << plan.l[p]) >> 1) - 1;
-        a.log_b = log_n - consumed;
-        DeviceTables::Split sp;
-        TF21_TRY(get_split_tables(tabs, a.log_b, inverse, &sp));
-        a.tw = ScaleTab{sp.lo, sp.hi, sp.h};
-        a.pre = cur_pre;
-        u64 grid = batch * a.n_outer * a.n_col_tiles;
-        if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-        u32 nt = pick_threads((u64)(1u << plan.l[p]) / 2 * kNttColTile);
-        TF21_LAUNCH(ntt_col_pass_kernel, (unsigned)grid, nt, col_pass_smem(plan.l[p]), st, a);
-        consumed += plan.l[p];
-        cur_src = scratch;
-        cur_src_words = array_words;
-        cur_n_in = n;
-        cur_pre = ScaleTab{nullptr, nullptr, 0};
-    }
-
-    RowPassArgs r{};
-    r.src = cur_src;
-    r.dst = dst;
-    r.src_array_words = cur_src_words;
-    r.dst_array_words = array_words;
-    r.log_nk = plan.l[plan.k - 1];
-    r.w = w;
-    const u32 nk = 1u << r.log_nk;
-    // rows per tile: keep the tile under ~150 KB of shared memory
-    u32 to = 16;
-    while (to > 1 && row_pass_smem(r.log_nk, to, w) > 150 * 1024) to--;
-    r.tw_nk = tw_small + (nk >> 1) - 1;
-    r.post = post;
-    r.post_scalar = post_scalar;
-    u64 grid;
-    if (plan.k == 1) {
-        r.single = 1;
-        if (batch > 0xffffffffull) return TF21_E_LEN_TOO_LARGE;
-        r.rows_total = (u32)batch;
-        if ((u64)to > batch) to = (u32)batch;
-        r.to = to;
-        r.n_tiles_t = (u32)((batch + to - 1) / to);
-        r.mid = 1;
-        r.src_t_stride = cur_src_words;
-        r.dst_t_stride = array_words;
-        r.dst_i_stride = w;
-        r.dst_mid_stride = 0;
-        r.elem_i_stride = 1;
-        r.elem_mid_stride = 0;
-        r.n_in_elems = cur_n_in;
-        r.pre = cur_pre;
-        // the batch index is folded into the t axis: arrays are addressed through t strides
-        r.src_array_words = 0;
-        r.dst_array_words = 0;
-        grid = r.n_tiles_t;
-    } else {
-        r.single = 0;
-        const u32 n1 = 1u << plan.l[0];
-        const u32 midc = (plan.k == 3) ? (1u << plan.l[1]) : 1u;
-        if (to > n1) to = n1;
-        // to must divide N_1 (power of two) so tiles never straddle
-        while (n1 % to) to--;
-        r.to = to;
-        r.rows_total = n1;
-        r.n_tiles_t = n1 / to;
-        r.mid = midc;
-        r.src_t_stride = (u64)midc * nk * w;       // consecutive i_1
-        r.dst_t_stride = w;
-        const u64 o_total = n >> r.log_nk;          // N_1 .. N_{k-1}
-        r.dst_i_stride = o_total * w;
-        r.dst_mid_stride = (u64)n1 * w;             // o' = i_1 + N_1 * i_2
-        r.elem_i_stride = o_total;
-        r.elem_mid_stride = n1;
-        r.n_in_elems = nk;
-        r.pre = ScaleTab{nullptr, nullptr, 0};
-        grid = batch * r.n_tiles_t * r.mid;
-    }
-    if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-    u32 nt = pick_threads((u64)nk / 2 * r.to * w);
-    TF21_LAUNCH(ntt_row_pass_kernel, (unsigned)grid, nt, row_pass_smem(r.log_nk, r.to, w), st, r);
-    return 0;
-}
-
 }  // namespace tf21

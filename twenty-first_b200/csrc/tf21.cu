@@ -1,7 +1,7 @@
 // tf21.cu -- the C ABI of libtf21 (include/tf21.h): argument checking, device state, host<->device
 // staging, and dispatch into the sm_100a kernels.  Single translation unit (the kernels live in the
 // included .cuh files) so the __constant__ tables are shared without relocatable device code.
-#include "ntt_kernels.cuh"
+#include "ntt_fast.cuh"
 #include "tip5_kernels.cuh"
 
 using namespace tf21;
@@ -9,9 +9,10 @@ using namespace tf21;
 namespace tf21 {
 
 // per-device state, created on first use of a device
-static int get_tables(DeviceTables **out) {
+static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
     int dev;
     TF21_TRY(current_device(&dev));
+    if (dev_out) *dev_out = dev;
     std::lock_guard<std::mutex> lock(g_mutex);
     DeviceTables &t = g_devices[dev];
     if (!t.constants_ready) {
@@ -19,6 +20,13 @@ static int get_tables(DeviceTables **out) {
         TF21_CUDA(cudaGetDeviceProperties(&prop, dev));
         t.sm_count = prop.multiProcessorCount;
         t.smem_optin = prop.sharedMemPerBlockOptin;
+        {   // keep stream-ordered scratch (cudaMallocAsync) cached across synchronisations: the default
+            // release threshold of 0 returns the memory to the OS at every sync and re-maps it per call
+            cudaMemPool_t pool;
+            TF21_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+            uint64_t thr = ~0ull;
+            TF21_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        }
         TF21_TRY(upload_tip5_constants());
         for (int inv = 0; inv < 2; inv++) {
             std::vector<u64> tw((1u << kNttMaxLogPass) - 1);
@@ -38,6 +46,12 @@ static int get_tables(DeviceTables **out) {
                                        (int)t.smem_optin));
         TF21_CUDA(cudaFuncSetAttribute(ntt_row_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)t.smem_optin));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         t.constants_ready = true;
     }
     *out = &t;
@@ -84,20 +98,11 @@ static int ntt_run_locked(DeviceTables &t, const u64 *src, u64 n_in, u64 *dst, u
         if (n == 1 && n_in == 0) TF21_CUDA(cudaMemsetAsync(dst, 0, batch * w * sizeof(u64), st));
         return 0;
     }
+    int dev;
+    TF21_TRY(current_device(&dev));
     Scratch scratch(st);
     if (ilog2_u64(n) > kNttMaxLogPass) TF21_TRY(scratch.alloc(n * w * batch));
-    {
-        // split-table construction mutates the cache
-        std::lock_guard<std::mutex> lock(g_mutex);
-        NttPlan plan = make_plan(ilog2_u64(n));
-        u32 consumed = 0;
-        for (u32 p = 0; p + 1 < plan.k; p++) {
-            DeviceTables::Split sp;
-            TF21_TRY(get_split_tables(t, ilog2_u64(n) - consumed, inverse, &sp));
-            consumed += plan.l[p];
-        }
-    }
-    return ntt_run(t, src, n_in, dst, n, w, batch, inverse, pre, post, post_scalar, scratch.p, st);
+    return ntt_run(t, dev, src, n_in, dst, n, w, batch, inverse, pre, post, post_scalar, scratch.p, st);
 }
 
 }  // namespace tf21
@@ -211,6 +216,18 @@ __global__ void selftest_field_kernel(int op, const u64 *a, const u64 *b, u64 *o
         case 3: r = gl_canon(x); break;
         case 4: r = gl_canon(gl_add_weak(x, y)); break;  // x any, y canonical
         case 5: r = gl_canon(gl_reduce96(x, (u32)y)); break;
+        case 6: r = gl_canon(gl_addl(x, y)); break;  // x any, y <= p
+        case 7: r = gl_canonw(x); break;
+        case 8: r = gl_canon(gl_sub(x, y)); break;   // x any, y < p
+#define TF21_SHL_CASE(S) case 100 + (S): r = gl_shlc(x, (S)); break;
+            TF21_SHL_CASE(3) TF21_SHL_CASE(6) TF21_SHL_CASE(9) TF21_SHL_CASE(12) TF21_SHL_CASE(15)
+            TF21_SHL_CASE(18) TF21_SHL_CASE(21) TF21_SHL_CASE(24) TF21_SHL_CASE(27) TF21_SHL_CASE(30)
+            TF21_SHL_CASE(33) TF21_SHL_CASE(36) TF21_SHL_CASE(39) TF21_SHL_CASE(42) TF21_SHL_CASE(45)
+            TF21_SHL_CASE(48) TF21_SHL_CASE(51) TF21_SHL_CASE(54) TF21_SHL_CASE(57) TF21_SHL_CASE(60)
+            TF21_SHL_CASE(63) TF21_SHL_CASE(66) TF21_SHL_CASE(69) TF21_SHL_CASE(72) TF21_SHL_CASE(75)
+            TF21_SHL_CASE(78) TF21_SHL_CASE(81) TF21_SHL_CASE(84) TF21_SHL_CASE(87) TF21_SHL_CASE(90)
+            TF21_SHL_CASE(93) TF21_SHL_CASE(1) TF21_SHL_CASE(31) TF21_SHL_CASE(95) TF21_SHL_CASE(65)
+#undef TF21_SHL_CASE
     }
     out[i] = r;
 }
