@@ -8,8 +8,13 @@
 //   t = circulant(MDS_MATRIX_FIRST_COLUMN) * s mod p                                (:154-157, naive.rs:54-68)
 //   s = t + ROUND_CONSTANTS[16 r + i] * 2^64 mod p                                  (:68-149, 178-180)
 // The MDS step follows the accumulator idea of the reference's AVX-512 path (avx512.rs:124-175):
-// split every lane into 32-bit halves, accumulate 16-bit x 32-bit products in 64-bit registers
-// (bounded by 2^52), seed the accumulators with the round-constant halves, reduce once.
+// split every lane into 32-bit halves, accumulate the 16-bit x 32-bit products per half, seed the
+// accumulators with the round-constant halves, reduce once.  On B200 the accumulation runs on the
+// FP64 pipe: every partial sum is an integer below 2^52 (sum of the MDS column = 524757 < 2^20,
+// times 2^32, plus a 32-bit round-constant half), so DFMA is exact, and it issues at one warp
+// instruction per 2 cycles per sub-partition next to the integer pipes -- whereas the 512
+// IMAD.WIDE per round of the integer formulation (one per 5.3 cycles, measured, tools/ubench.cu)
+// made the whole permutation FMA-pipe bound.  Conversions use the 2^52 bias trick (no I2F/F2I).
 #pragma once
 #include "field.cuh"
 
@@ -21,8 +26,8 @@
 
 // Filled by upload_tip5_constants (tip5_kernels.cuh): raw round constants split in 32-bit halves,
 // zero-extended to u64, and the S-box table.
-__constant__ u64 c_tip5_rc_lo[TIP5_ROUNDS * TIP5_STATE];
-__constant__ u64 c_tip5_rc_hi[TIP5_ROUNDS * TIP5_STATE];
+__constant__ double c_tip5_rc_lo[TIP5_ROUNDS * TIP5_STATE];
+__constant__ double c_tip5_rc_hi[TIP5_ROUNDS * TIP5_STATE];
 __constant__ uint8_t c_tip5_lut[256];
 
 // MDS_MATRIX_FIRST_COLUMN, tip5/mod.rs:154-157
@@ -68,28 +73,30 @@ __device__ __forceinline__ void tip5_permutation(u64 (&s)[TIP5_STATE], const uin
             u64 x6 = gl_mul(x2, x4);
             s[i] = gl_mul(x, x6);
         }
-        // ---- MDS + round constants ----
-        u64 acc_lo[TIP5_STATE], acc_hi[TIP5_STATE];
-#pragma unroll
-        for (int i = 0; i < TIP5_STATE; i++) {
-            acc_lo[i] = c_tip5_rc_lo[r * TIP5_STATE + i];
-            acc_hi[i] = c_tip5_rc_hi[r * TIP5_STATE + i];
-        }
+        // ---- MDS + round constants (exact integer arithmetic on the FP64 pipe) ----
+        const double kBias = 4503599627370496.0;  // 2^52
+        double dl[TIP5_STATE], dh[TIP5_STATE];
 #pragma unroll
         for (int j = 0; j < TIP5_STATE; j++) {
-            u32 lo = (u32)s[j], hi = (u32)(s[j] >> 32);
-#pragma unroll
-            for (int i = 0; i < TIP5_STATE; i++) {
-                const u32 m = TIP5_MDS((i - j) & 15);
-                acc_lo[i] += (u64)lo * m;
-                acc_hi[i] += (u64)hi * m;
-            }
+            dl[j] = __hiloint2double(0x43300000, (int)(u32)s[j]) - kBias;
+            dh[j] = __hiloint2double(0x43300000, (int)(u32)(s[j] >> 32)) - kBias;
         }
 #pragma unroll
         for (int i = 0; i < TIP5_STATE; i++) {
-            // value = acc_lo + acc_hi * 2^32, acc_* < 2^53
-            u64 x0 = acc_lo[i] + (acc_hi[i] << 32);
-            u32 x1 = (u32)(acc_hi[i] >> 32) + (x0 < acc_lo[i] ? 1u : 0u);
+            double al = c_tip5_rc_lo[r * TIP5_STATE + i];
+            double ah = c_tip5_rc_hi[r * TIP5_STATE + i];
+#pragma unroll
+            for (int j = 0; j < TIP5_STATE; j++) {
+                const double m = (double)TIP5_MDS((i - j) & 15);
+                al = fma(m, dl[j], al);
+                ah = fma(m, dh[j], ah);
+            }
+            // al, ah < 2^52: adding 2^52 leaves the integer in the 52 mantissa bits
+            const u64 acc_lo = (u64)__double_as_longlong(al + kBias) & 0x000FFFFFFFFFFFFFull;
+            const u64 acc_hi = (u64)__double_as_longlong(ah + kBias) & 0x000FFFFFFFFFFFFFull;
+            // value = acc_lo + acc_hi * 2^32
+            u64 x0 = acc_lo + (acc_hi << 32);
+            u32 x1 = (u32)(acc_hi >> 32) + (x0 < acc_lo ? 1u : 0u);
             u64 v = gl_reduce96(x0, x1);
             s[i] = (i < 4) ? gl_canon(v) : v;
         }

@@ -41,11 +41,11 @@ static const u64 kTip5RoundConstants[TIP5_ROUNDS * TIP5_STATE] = {
 };
 
 inline int upload_tip5_constants() {
-    u64 lo[TIP5_ROUNDS * TIP5_STATE], hi[TIP5_ROUNDS * TIP5_STATE];
+    double lo[TIP5_ROUNDS * TIP5_STATE], hi[TIP5_ROUNDS * TIP5_STATE];
     for (int i = 0; i < TIP5_ROUNDS * TIP5_STATE; i++) {
         u64 raw = hgl_to_raw(kTip5RoundConstants[i]);
-        lo[i] = raw & 0xffffffffull;
-        hi[i] = raw >> 32;
+        lo[i] = (double)(raw & 0xffffffffull);  // 32-bit halves: exact in a double
+        hi[i] = (double)(raw >> 32);
     }
     uint8_t lut[256];
     // LOOKUP_TABLE, tip5/mod.rs:50-64 = ((x+1)^3 + 256) mod 257 (tip5/mod.rs:1022-1053)
