@@ -113,7 +113,7 @@ def test_ntt_reference_kats(tf, oracle, kats):
     assert np.array_equal(x, orig)
 
 
-@pytest.mark.parametrize("log2n", list(range(0, 15)) + [16, 18, 20, 21])
+@pytest.mark.parametrize("log2n", list(range(0, 25)))
 def test_bfe_ntt_matches_oracle(tf, oracle, log2n):
     n = 1 << log2n
     inputs = [rnd(100 + log2n, n)] + (adversarial(n) if log2n <= 12 or log2n == 20 else [])
@@ -133,7 +133,7 @@ def test_bfe_ntt_matches_oracle(tf, oracle, log2n):
         assert np.array_equal(got, x)
 
 
-@pytest.mark.parametrize("log2n", list(range(0, 13)) + [15, 20, 22])
+@pytest.mark.parametrize("log2n", list(range(0, 23)))
 def test_xfe_ntt_matches_oracle(tf, oracle, log2n):
     n = 1 << log2n
     inputs = [rnd(200 + log2n, 3 * n)] + (adversarial(n, 3) if log2n <= 10 else [])
@@ -169,7 +169,7 @@ def test_ntt_edge_cases_and_errors(tf):
     assert api is not None
 
 
-@pytest.mark.parametrize("log2n,width,batch", [(3, 1, 5), (10, 1, 33), (10, 3, 7), (12, 1, 9), (16, 1, 4), (20, 1, 3), (11, 3, 5)])
+@pytest.mark.parametrize("log2n,width,batch", [(3, 1, 5), (10, 1, 33), (10, 3, 7), (12, 1, 9), (16, 1, 4), (20, 1, 3), (11, 3, 5), (13, 3, 3), (17, 1, 3), (21, 3, 2)])
 def test_batched_ntt_matches_oracle(tf, oracle, log2n, width, batch):
     api = importlib.import_module("twenty-first_b200.api")
     n = 1 << log2n
@@ -212,7 +212,7 @@ def test_ntt_linearity_and_impulse_at_2_20(tf, oracle):
 
 
 # ---- coset ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("log_coeffs,log_order,width", [(0, 0, 1), (0, 3, 1), (3, 3, 1), (5, 9, 1), (10, 10, 3), (8, 12, 3), (12, 16, 1), (14, 21, 1), (13, 17, 3)])
+@pytest.mark.parametrize("log_coeffs,log_order,width", [(0, 0, 1), (0, 3, 1), (3, 3, 1), (5, 9, 1), (10, 10, 3), (8, 12, 3), (12, 16, 1), (14, 21, 1), (13, 17, 3), (16, 20, 3), (18, 22, 1)])
 def test_coset_evaluate_interpolate_match_oracle(tf, oracle, log_coeffs, log_order, width):
     nc, order = 1 << log_coeffs, 1 << log_order
     coeffs = rnd(400 + log_coeffs * 31 + log_order, nc * width)
@@ -244,7 +244,7 @@ def test_coset_evaluate_degree_rules(tf, oracle):
     assert not z.any()
 
 
-@pytest.mark.parametrize("log_in,log_out,width", [(0, 0, 1), (0, 4, 3), (4, 4, 1), (6, 10, 3), (10, 14, 1), (12, 16, 3), (16, 20, 3)])
+@pytest.mark.parametrize("log_in,log_out,width", [(0, 0, 1), (0, 4, 3), (4, 4, 1), (6, 10, 3), (10, 14, 1), (12, 16, 3), (16, 20, 3), (18, 22, 3), (13, 13, 1)])
 def test_coset_lde_matches_oracle(tf, oracle, log_in, log_out, width):
     n_in, n_out = 1 << log_in, 1 << log_out
     values = rnd(500 + log_in + log_out, n_in * width)

@@ -35,21 +35,29 @@ constexpr size_t kFastSmem = (size_t)kFastCols * kFastS * sizeof(u64);
 __host__ __device__ constexpr u32 brev5(u32 k) {
     return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
 }
+__host__ __device__ constexpr u32 brev_bits(u32 k, int bits) {
+    u32 r = 0;
+    for (int i = 0; i < bits; i++) r |= ((k >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
 
-// 32-point DFT in registers, decimation in time: in v[a] = x[a] (any u64), out v[brev5(k)] =
-// sum_a x[a] w^(a k) (any u64), w = omega_32^(+-1) = 2^(+-78).  (butterfly of ntt.rs:203-210;
-// the twiddles are shifts; exponents >= 96 use 2^96 = -1 and swap the roles of sum and difference)
-template <bool INV>
-__device__ __forceinline__ void dft32(u64 (&v)[32]) {
+// 2^A-point DFT in registers (A <= 6), decimation in time: in v[a] = x[a] (any u64), out
+// v[brev_A(k)] = sum_a x[a] w^(a k) (any u64), w = omega_{2^A}^(+-1) = 2^(+-39 * 2^(6-A)) because
+// omega_64 = 2^39 (PRIMITIVE_ROOTS, b_field_element.rs:43-78).  (butterfly of ntt.rs:203-210; the
+// twiddles are shifts; exponents >= 96 use 2^96 = -1 and swap the roles of sum and difference)
+template <bool INV, int A>
+__device__ __forceinline__ void dft_pow2(u64 (&v)[1 << A]) {
+    constexpr int N = 1 << A;
+    constexpr int EU = (39 << (6 - A)) % 192;
 #pragma unroll
-    for (int ls = 1; ls <= 5; ls++) {
+    for (int ls = 1; ls <= A; ls++) {
         const int m = 1 << ls, half = m >> 1;
 #pragma unroll
-        for (int k = 0; k < 32; k += m) {
+        for (int k = 0; k < N; k += m) {
 #pragma unroll
             for (int j = 0; j < half; j++) {
-                const int iu = brev5(k + j), ib = brev5(k + j + half);
-                int E = (78 * j * (32 / m)) % 192;
+                const int iu = brev_bits(k + j, A), ib = brev_bits(k + j + half, A);
+                int E = (EU * j * (N / m)) % 192;
                 if (INV) E = (192 - E) % 192;
                 const bool neg = E >= 96;
                 const int S = neg ? E - 96 : E;
@@ -65,6 +73,16 @@ __device__ __forceinline__ void dft32(u64 (&v)[32]) {
             }
         }
     }
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft32(u64 (&v)[32]) {
+    dft_pow2<INV, 5>(v);
+}
+
+// lazy twiddle from split tables (any u64 representative)
+__device__ __forceinline__ u64 scale_factor_l(const ScaleTab &t, u64 idx) {
+    return gl_mul(__ldg(t.lo + (idx & ((1ull << t.h) - 1))), __ldg(t.hi + (idx >> t.h)));
 }
 
 // The 1024-point DFT of the column held by this warp.
@@ -179,49 +197,124 @@ __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_col_kernel(const Fast
 struct FastRowArgs {
     const u64 *src;
     u64 *dst;
-    u64 array_words;      // n (w = 1)
-    u32 n_tiles_t, mid;   // tiles of 8 consecutive i_1; number of mid values
-    u64 src_t_stride;     // words between consecutive i_1 rows
-    u64 dst_i_stride, dst_mid_stride;
+    u64 array_words;      // n * w
+    u32 w;
+    u32 n1, n2, n3;       // sizes of the leading digits i_1, i_2, i_3 (1 when absent); rows = n1 n2 n3
+    u32 n_tiles;          // rows * w / 8
     const u64 *t1;
     u64 post_scalar;      // 0 => none
     ScaleTab post;
-    u64 elem_i_stride, elem_mid_stride;
 };
 
-// Last pass of a multi-pass transform, w = 1: rows are contiguous (direct coalesced loads), the
-// output is transposed (consecutive i_1 adjacent) and goes through shared memory; canonical on store.
+// Last pass of a multi-pass transform.  The passes before it are position preserving, so the source
+// is [i_1][i_2][i_3][j_k][w] with contiguous 1024-element rows; the output index is
+// o' + rows * i_k with o' = i_1 + n1 (i_2 + n2 i_3) (digit reversal of the row index).  A CTA takes 8
+// consecutive word-columns tc = o' * w + c of the output; a warp loads its row directly (stride w),
+// the transposed store goes through shared memory; canonical on store.
 template <bool INV>
 __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_row_kernel(const FastRowArgs a) {
     extern __shared__ u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 tt = blockIdx.x % a.n_tiles_t;
-    const u32 rest = blockIdx.x / a.n_tiles_t;
-    const u32 mid = rest % a.mid, b = rest / a.mid;
-    const u32 t0 = tt * kFastCols;
-
-    const u64 *row = a.src + (u64)b * a.array_words + (u64)(t0 + warp) * a.src_t_stride + (u64)mid * 1024;
-    u64 v[32];
+    const u32 tile_id = blockIdx.x % a.n_tiles;
+    const u32 b = blockIdx.x / a.n_tiles;
+    const u32 tc0 = tile_id * kFastCols;
+    const u32 rows = a.n1 * a.n2 * a.n3;
+    {
+        const u32 tc = tc0 + warp;
+        const u32 op = tc / a.w, c = tc - op * a.w;
+        const u32 i1 = op % a.n1, r23 = op / a.n1;
+        const u32 i2 = r23 % a.n2, i3 = r23 / a.n2;
+        const u64 rho = ((u64)i1 * a.n2 + i2) * a.n3 + i3;
+        const u64 *row = a.src + (u64)b * a.array_words + rho * 1024 * a.w + c;
+        u64 v[32];
 #pragma unroll
-    for (int aa = 0; aa < 32; aa++) v[aa] = row[32 * aa + lane];
-    u64 *slice = tile + warp * kFastS;
-    dft1024_warp<INV>(v, slice, a.t1 + lane, nullptr, lane);
+        for (int aa = 0; aa < 32; aa++) v[aa] = row[(u64)(32 * aa + lane) * a.w];
+        dft1024_warp<INV>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane);
+    }
     __syncthreads();
 
-    // stage out: element (i_1 = t0 + c, i_k = r) -> dst[r * dst_i_stride + (t0 + c)]
+    // stage out: word (i_k = r, tc) -> dst[r * rows * w + tc]
     {
-        const u32 c = lane & 7, rsub = lane >> 3;
-        u64 *dst = a.dst + (u64)b * a.array_words + (u64)mid * a.dst_mid_stride + t0 + c;
-        const u64 *tl = tile + c * kFastS;
-        const u64 elem_base = (u64)(t0 + c) + (u64)mid * a.elem_mid_stride;
+        const u32 c8 = lane & 7, rsub = lane >> 3;
+        const u32 tc = tc0 + c8;
+        u64 *dst = a.dst + (u64)b * a.array_words + tc;
+        const u64 *tl = tile + c8 * kFastS;
+        const u64 ostride = (u64)rows * a.w;
+        const u64 op = tc / a.w;  // element index = op + rows * r
 #pragma unroll 8
         for (u32 it = 0; it < 32; it++) {
             const u32 r = warp * 128 + it * 4 + rsub;
             u64 x = tl[r];
             if (a.post_scalar) x = gl_mul(x, a.post_scalar);
-            if (a.post.lo) x = gl_mul(x, scale_factor(a.post, elem_base + (u64)r * a.elem_i_stride));
-            dst[(u64)r * a.dst_i_stride] = gl_canonw(x);
+            if (a.post.lo) x = gl_mul(x, scale_factor_l(a.post, op + (u64)rows * r));
+            dst[(u64)r * ostride] = gl_canonw(x);
+        }
+    }
+}
+
+struct SmallColArgs {
+    const u64 *src;
+    u64 *dst;
+    u64 src_array_words, dst_array_words;
+    u32 w;
+    u64 inner_words;     // multiple of 128
+    u32 n_outer;
+    u64 n_in_elems;
+    const u64 *tw_full;  // [N_p][inner_elems] scalar * omega_B^(i j) (B <= 2^20) or nullptr
+    ScaleTab tw;         // split tables for omega_B^e, used when tw_full == nullptr
+    u64 tw_scalar;       // extra factor on every output of the split path (n^-1), 0 => none
+    ScaleTab pre;
+};
+
+// Column pass of 2^A <= 64 points: one THREAD owns one word-column (adjacent threads own adjacent
+// columns, so every access is fully coalesced and nothing goes through shared memory); the whole
+// transform uses shift twiddles; then the inter-pass twiddle omega_B^(i * j_rest).
+template <bool INV, int A>
+__global__ void __launch_bounds__(128) ntt_small_col_kernel(const SmallColArgs a) {
+    constexpr int NP = 1 << A;
+    const u64 gid = (u64)blockIdx.x * 128 + threadIdx.x;
+    const u64 q = gid % a.inner_words;
+    const u64 rest = gid / a.inner_words;
+    const u32 o = (u32)(rest % a.n_outer);
+    const u64 b = rest / a.n_outer;
+    const u64 inner_elems = a.inner_words / a.w;
+    const u64 jcol = q / a.w;
+    const u64 off = (u64)o * NP * a.inner_words + q;
+    const u64 *src = a.src + b * a.src_array_words + off;
+    u64 v[NP];
+#pragma unroll
+    for (int r = 0; r < NP; r++) {
+        const u64 j = ((u64)o * NP + r) * inner_elems + jcol;
+        u64 x = 0;
+        if (j < a.n_in_elems) {
+            x = src[(u64)r * a.inner_words];
+            if (a.pre.lo) x = gl_mul(x, scale_factor_l(a.pre, j));
+        }
+        v[r] = x;
+    }
+    dft_pow2<INV, A>(v);
+    u64 *dst = a.dst + b * a.dst_array_words + off;
+    if (a.tw_full) {
+        const u64 *tcol = a.tw_full + jcol;  // consecutive threads read consecutive entries
+#pragma unroll
+        for (int i = 0; i < NP; i++)
+            dst[(u64)i * a.inner_words] = gl_mul(v[brev_bits(i, A)], __ldg(tcol + (u64)i * inner_elems));
+    } else {
+        // B > 2^20: no full table.  g = omega_B^jcol from the split tables (coalesced: the index is the
+        // column), then scalar * g^i by four interleaved power chains -- no gathers.
+        const u64 g = scale_factor_l(a.tw, jcol);
+        u64 pw[4];
+        pw[0] = a.tw_scalar ? a.tw_scalar : 1ull;
+        pw[1] = gl_mul(pw[0], g);
+        pw[2] = gl_mul(pw[1], g);
+        pw[3] = gl_mul(pw[2], g);
+        const u64 g2 = gl_mul(g, g);
+        const u64 g4 = gl_mul(g2, g2);
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            if (i >= 4) pw[i & 3] = gl_mul(pw[i & 3], g4);
+            dst[(u64)i * a.inner_words] = gl_mul(v[brev_bits(i, A)], pw[i & 3]);
         }
     }
 }
@@ -272,8 +365,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_single_kernel(const F
 
 // ---- tables for the fast path ---------------------------------------------------------------------
 struct FastTables {
-    std::map<int, u64 *> t1;                                   // inverse -> [32][32]
-    std::map<std::tuple<unsigned, int, u64>, u64 *> tw_full;   // (log_b, inverse, scalar) -> [B/1024][1024]
+    std::map<int, u64 *> t1;                                             // inverse -> [32][32]
+    std::map<std::tuple<unsigned, unsigned, int, u64>, u64 *> tw_full;   // (log_b, log_np, inverse, scalar)
+    std::map<std::tuple<unsigned, unsigned, int, u64>, u64 *> tw_small;  // same key, [N_p][B / N_p] layout
 };
 static std::map<int, FastTables> g_fast_tables;  // by device, guarded by g_mutex
 
@@ -303,10 +397,11 @@ inline int get_t1(DeviceTables &t, int dev, int inverse, const u64 **out) {
 
 constexpr unsigned kFullTwiddleMaxLog = 20;  // 8 MiB per (size, direction): stays resident in L2
 
-// T[j][i] = scalar * omega_B^(+-j i), j < B/1024, i < 1024
-inline int get_tw_full(DeviceTables &t, int dev, unsigned log_b, int inverse, u64 scalar, const u64 **out) {
+// T[j][i] = scalar * omega_B^(+-j i), j < B / N_p, i < N_p = 2^log_np
+inline int get_tw_full(DeviceTables &t, int dev, unsigned log_b, unsigned log_np, int inverse, u64 scalar,
+                       const u64 **out) {
     FastTables &ft = g_fast_tables[dev];
-    auto key = std::make_tuple(log_b, inverse, scalar);
+    auto key = std::make_tuple(log_b, log_np, inverse, scalar);
     auto it = ft.tw_full.find(key);
     if (it != ft.tw_full.end()) {
         *out = it->second;
@@ -314,13 +409,14 @@ inline int get_tw_full(DeviceTables &t, int dev, unsigned log_b, int inverse, u6
     }
     u64 w = hgl_root_of_unity(log_b);
     if (inverse) w = hgl_inv(w);
-    const u64 rows = (1ull << log_b) >> 10;
-    std::vector<u64> h(rows * 1024);
+    const u64 cols = 1ull << log_np;
+    const u64 rows = (1ull << log_b) >> log_np;
+    std::vector<u64> h(rows * cols);
     u64 step = 1;  // w^j
     for (u64 j = 0; j < rows; j++) {
         u64 acc = scalar % GL_P;
-        for (u32 i = 0; i < 1024; i++) {
-            h[j * 1024 + i] = acc;
+        for (u64 i = 0; i < cols; i++) {
+            h[j * cols + i] = acc;
             acc = hgl_mul(acc, step);
         }
         step = hgl_mul(step, w);
@@ -332,28 +428,65 @@ inline int get_tw_full(DeviceTables &t, int dev, unsigned log_b, int inverse, u6
     return 0;
 }
 
+// small column passes: T[i][j] = scalar * omega_B^(+-i j), i < N_p = 2^log_np, j < B / N_p
+inline int get_tw_small(DeviceTables &t, int dev, unsigned log_b, unsigned log_np, int inverse, u64 scalar,
+                        const u64 **out) {
+    FastTables &ft = g_fast_tables[dev];
+    auto key = std::make_tuple(log_b, log_np, inverse, scalar);
+    auto it = ft.tw_small.find(key);
+    if (it != ft.tw_small.end()) {
+        *out = it->second;
+        return 0;
+    }
+    u64 w = hgl_root_of_unity(log_b);
+    if (inverse) w = hgl_inv(w);
+    const u64 rows = 1ull << log_np;
+    const u64 cols = (1ull << log_b) >> log_np;
+    std::vector<u64> h(rows * cols);
+    u64 step = 1;  // w^i
+    for (u64 i = 0; i < rows; i++) {
+        u64 acc = scalar % GL_P;
+        for (u64 j = 0; j < cols; j++) {
+            h[i * cols + j] = acc;
+            acc = hgl_mul(acc, step);
+        }
+        step = hgl_mul(step, w);
+    }
+    u64 *d;
+    TF21_TRY(upload(t, h, &d));
+    ft.tw_small[key] = d;
+    *out = d;
+    return 0;
+}
+
 template <typename K, typename A>
 inline int launch_fast(K kernel, unsigned grid, const A &args, cudaStream_t st) {
     TF21_LAUNCH(kernel, grid, kFastThreads, kFastSmem, st, args);
     return 0;
 }
 
-// Core entry: dst[b] = scale_post( NTT_n( zero_extend( scale_pre( src[b][0..n_in) ) ) ) ) for b < batch.
-// src arrays are n_in*w words apart, dst arrays n*w words apart.  src == dst is allowed when
-// n_in == n.  `scratch` (n*w*batch words) is required when log2 n > 10.  Caller holds no lock;
-// table lookups lock g_mutex internally.
-inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *dst, u64 n, u32 w, u64 batch,
-                   int inverse, ScaleTab pre, ScaleTab post, u64 post_scalar, u64 *scratch, cudaStream_t st) {
+template <bool INV>
+inline int launch_small(u32 a_log, unsigned grid, const SmallColArgs &args, cudaStream_t st) {
+    switch (a_log) {
+        case 1: TF21_LAUNCH((ntt_small_col_kernel<INV, 1>), grid, 128, 0, st, args); break;
+        case 2: TF21_LAUNCH((ntt_small_col_kernel<INV, 2>), grid, 128, 0, st, args); break;
+        case 3: TF21_LAUNCH((ntt_small_col_kernel<INV, 3>), grid, 128, 0, st, args); break;
+        case 4: TF21_LAUNCH((ntt_small_col_kernel<INV, 4>), grid, 128, 0, st, args); break;
+        case 5: TF21_LAUNCH((ntt_small_col_kernel<INV, 5>), grid, 128, 0, st, args); break;
+        case 6: TF21_LAUNCH((ntt_small_col_kernel<INV, 6>), grid, 128, 0, st, args); break;
+        default: return TF21_E_BAD_ARG;
+    }
+    return 0;
+}
+
+// generic (shared-memory radix-2) path: sizes below 2^13 and width-3 single passes
+inline int ntt_run_generic(DeviceTables &tabs, const u64 *src, u64 n_in, u64 *dst, u64 n, u32 w, u64 batch,
+                           int inverse, ScaleTab pre, ScaleTab post, u64 post_scalar, u64 *scratch,
+                           cudaStream_t st) {
     const u32 log_n = ilog2_u64(n);
     const NttPlan plan = make_plan(log_n);
     const u64 array_words = n * w;
     const u64 *tw_small = tabs.tw_small[inverse ? 1 : 0];
-    const u64 *t1 = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(g_mutex);
-        TF21_TRY(get_t1(tabs, dev, inverse, &t1));
-    }
-
     const u64 *cur_src = src;
     u64 cur_src_words = n_in * w;
     u64 cur_n_in = n_in;
@@ -365,67 +498,30 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         const u32 log_b = log_n - consumed;
         const u64 inner_words = ((u64)1 << log_inner) * w;
         const u32 n_outer = 1u << consumed;
-        if (lp == 10) {
-            FastColArgs a{};
-            a.src = cur_src;
-            a.dst = scratch;
-            a.src_array_words = cur_src_words;
-            a.dst_array_words = array_words;
-            a.w = w;
-            a.inner_words = inner_words;
-            a.n_col_tiles = (u32)(inner_words / kFastCols);
-            a.n_outer = n_outer;
-            a.n_in_elems = cur_n_in;
-            a.t1 = t1;
-            a.log_b = log_b;
-            a.pre = cur_pre;
-            {
-                std::lock_guard<std::mutex> lock(g_mutex);
-                if (log_b <= kFullTwiddleMaxLog) {
-                    u64 scalar = 1;
-                    if (p == 0 && post_scalar) {  // fold the unscale (ntt.rs:220-228) into pass 1
-                        scalar = post_scalar;
-                        post_scalar = 0;
-                    }
-                    TF21_TRY(get_tw_full(tabs, dev, log_b, inverse, scalar, &a.tw_full));
-                } else {
-                    DeviceTables::Split sp;
-                    TF21_TRY(get_split_tables(tabs, log_b, inverse, &sp));
-                    a.tw = ScaleTab{sp.lo, sp.hi, sp.h};
-                }
-            }
-            u64 grid = batch * n_outer * a.n_col_tiles;
-            if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-            if (inverse)
-                TF21_TRY(launch_fast(ntt1024_col_kernel<true>, (unsigned)grid, a, st));
-            else
-                TF21_TRY(launch_fast(ntt1024_col_kernel<false>, (unsigned)grid, a, st));
-        } else {
-            ColPassArgs a{};
-            a.src = cur_src;
-            a.dst = scratch;
-            a.src_array_words = cur_src_words;
-            a.dst_array_words = array_words;
-            a.log_np = lp;
-            a.w = w;
-            a.inner_words = inner_words;
-            a.n_col_tiles = (u32)((inner_words + kNttColTile - 1) / kNttColTile);
-            a.n_outer = n_outer;
-            a.n_in_elems = cur_n_in;
-            a.tw_np = tw_small + ((1u << lp) >> 1) - 1;
-            a.log_b = log_b;
-            DeviceTables::Split sp;
-            {
-                std::lock_guard<std::mutex> lock(g_mutex);
-                TF21_TRY(get_split_tables(tabs, log_b, inverse, &sp));
-            }
-            a.tw = ScaleTab{sp.lo, sp.hi, sp.h};
-            a.pre = cur_pre;
-            u64 grid = batch * n_outer * a.n_col_tiles;
-            if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-            u32 nt = pick_threads((u64)(1u << lp) / 2 * kNttColTile);
-            TF21_LAUNCH(ntt_col_pass_kernel, (unsigned)grid, nt, col_pass_smem(lp), st, a);
+        ColPassArgs a{};
+        a.src = cur_src;
+        a.dst = scratch;
+        a.src_array_words = cur_src_words;
+        a.dst_array_words = array_words;
+        a.log_np = lp;
+        a.w = w;
+        a.inner_words = inner_words;
+        a.n_col_tiles = (u32)((inner_words + kNttColTile - 1) / kNttColTile);
+        a.n_outer = n_outer;
+        a.n_in_elems = cur_n_in;
+        a.tw_np = tw_small + ((1u << lp) >> 1) - 1;
+        a.log_b = log_b;
+        DeviceTables::Split sp;
+        {
+            std::lock_guard<std::mutex> lock(g_mutex);
+            TF21_TRY(get_split_tables(tabs, log_b, inverse, &sp));
         }
+        a.tw = ScaleTab{sp.lo, sp.hi, sp.h};
+        a.pre = cur_pre;
+        u64 grid = batch * n_outer * a.n_col_tiles;
+        if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+        u32 nt = pick_threads((u64)(1u << lp) / 2 * kNttColTile);
+        TF21_LAUNCH(ntt_col_pass_kernel, (unsigned)grid, nt, col_pass_smem(lp), st, a);
         consumed += lp;
         cur_src = scratch;
         cur_src_words = array_words;
@@ -435,47 +531,6 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
 
     const u32 lk = plan.l[plan.k - 1];
     const u32 nk = 1u << lk;
-    if (lk == 10 && w == 1 && plan.k == 1) {
-        FastSingleArgs a{};
-        a.src = cur_src;
-        a.dst = dst;
-        a.src_array_words = cur_src_words;
-        a.dst_array_words = array_words;
-        a.batch = batch;
-        a.n_in_elems = cur_n_in;
-        a.t1 = t1;
-        a.post_scalar = post_scalar;
-        a.pre = cur_pre;
-        a.post = post;
-        u64 grid = (batch + kFastCols - 1) / kFastCols;
-        if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-        if (inverse) return launch_fast(ntt1024_single_kernel<true>, (unsigned)grid, a, st);
-        return launch_fast(ntt1024_single_kernel<false>, (unsigned)grid, a, st);
-    }
-    if (lk == 10 && w == 1 && plan.k >= 2 && plan.l[0] >= 3) {
-        FastRowArgs a{};
-        const u32 n1 = 1u << plan.l[0];
-        const u32 midc = (plan.k == 3) ? (1u << plan.l[1]) : 1u;
-        const u64 o_total = n >> lk;
-        a.src = cur_src;
-        a.dst = dst;
-        a.array_words = array_words;
-        a.n_tiles_t = n1 / kFastCols;
-        a.mid = midc;
-        a.src_t_stride = (u64)midc * 1024;
-        a.dst_i_stride = o_total;
-        a.dst_mid_stride = n1;
-        a.t1 = t1;
-        a.post_scalar = post_scalar;
-        a.post = post;
-        a.elem_i_stride = o_total;
-        a.elem_mid_stride = n1;
-        u64 grid = batch * a.n_tiles_t * a.mid;
-        if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-        if (inverse) return launch_fast(ntt1024_row_kernel<true>, (unsigned)grid, a, st);
-        return launch_fast(ntt1024_row_kernel<false>, (unsigned)grid, a, st);
-    }
-
     RowPassArgs r{};
     r.src = cur_src;
     r.dst = dst;
@@ -535,6 +590,168 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     u32 nt = pick_threads((u64)nk / 2 * r.to * w);
     TF21_LAUNCH(ntt_row_pass_kernel, (unsigned)grid, nt, row_pass_smem(r.log_nk, r.to, w), st, r);
     return 0;
+}
+
+// Core entry: dst[b] = scale_post( NTT_n( zero_extend( scale_pre( src[b][0..n_in) ) ) ) ) for b < batch.
+// src arrays are n_in*w words apart, dst arrays n*w words apart.  src == dst is allowed when
+// n_in == n.  `scratch` (n*w*batch words) is required when log2 n > 10.  Caller holds no lock;
+// table lookups lock g_mutex internally.
+//
+// Pass plan for n >= 2^13 (register-resident kernels only):
+//   [ one or two "small" column passes of 2^a <= 64 points ]  [ a 1024-point column pass if log2 n >= 20 ]
+//   [ the 1024-point transposing row pass ]
+// e.g. 2^20 = 1024 x 1024, 2^22 = 4 x 1024 x 1024, 2^26 = 64 x 1024 x 1024, 2^16 = 64 x 1024.
+inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *dst, u64 n, u32 w, u64 batch,
+                   int inverse, ScaleTab pre, ScaleTab post, u64 post_scalar, u64 *scratch, cudaStream_t st) {
+    const u32 log_n = ilog2_u64(n);
+    const u64 array_words = n * w;
+    if (log_n < 10 || (log_n == 10 && w != 1) || log_n == 11 || log_n == 12)
+        return ntt_run_generic(tabs, src, n_in, dst, n, w, batch, inverse, pre, post, post_scalar, scratch, st);
+
+    const u64 *t1 = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        TF21_TRY(get_t1(tabs, dev, inverse, &t1));
+    }
+    if (log_n == 10) {
+        FastSingleArgs a{};
+        a.src = src;
+        a.dst = dst;
+        a.src_array_words = n_in * w;
+        a.dst_array_words = array_words;
+        a.batch = batch;
+        a.n_in_elems = n_in;
+        a.t1 = t1;
+        a.post_scalar = post_scalar;
+        a.pre = pre;
+        a.post = post;
+        u64 grid = (batch + kFastCols - 1) / kFastCols;
+        if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+        if (inverse) return launch_fast(ntt1024_single_kernel<true>, (unsigned)grid, a, st);
+        return launch_fast(ntt1024_single_kernel<false>, (unsigned)grid, a, st);
+    }
+
+    // ---- plan: logs of the leading (column) passes, the last pass is always the 1024-point row pass ----
+    u32 lead[3];
+    u32 n_lead = 0;
+    bool lead_is_col10[3] = {false, false, false};
+    {
+        u32 rem = log_n - 10;
+        const bool has_col = rem >= 10;
+        if (has_col) rem -= 10;
+        if (rem > 6) {
+            lead[n_lead++] = (rem + 1) / 2;
+            lead[n_lead++] = rem / 2;
+        } else if (rem > 0) {
+            lead[n_lead++] = rem;
+        }
+        if (has_col) {
+            lead_is_col10[n_lead] = true;
+            lead[n_lead++] = 10;
+        }
+    }
+
+    const u64 *cur_src = src;
+    u64 cur_src_words = n_in * w;
+    u64 cur_n_in = n_in;
+    ScaleTab cur_pre = pre;
+    u32 consumed = 0;
+    for (u32 p = 0; p < n_lead; p++) {
+        const u32 lp = lead[p];
+        const u32 log_inner = log_n - consumed - lp;
+        const u32 log_b = log_n - consumed;
+        const u64 inner_words = ((u64)1 << log_inner) * w;
+        const u32 n_outer = 1u << consumed;
+        u64 scalar = 1;
+        if (p == 0 && post_scalar) {  // fold the unscale (ntt.rs:220-228) into the first twiddle table
+            scalar = post_scalar;
+            post_scalar = 0;
+        }
+        const u64 *tw_full = nullptr;
+        ScaleTab tw{nullptr, nullptr, 0};
+        u64 tw_scalar = 0;
+        {
+            std::lock_guard<std::mutex> lock(g_mutex);
+            if (log_b <= kFullTwiddleMaxLog) {
+                if (lead_is_col10[p])
+                    TF21_TRY(get_tw_full(tabs, dev, log_b, lp, inverse, scalar, &tw_full));
+                else
+                    TF21_TRY(get_tw_small(tabs, dev, log_b, lp, inverse, scalar, &tw_full));
+            } else {
+                DeviceTables::Split sp;
+                TF21_TRY(get_split_tables(tabs, log_b, inverse, &sp));
+                tw = ScaleTab{sp.lo, sp.hi, sp.h};
+                tw_scalar = scalar == 1 ? 0 : scalar;
+            }
+        }
+        if (lead_is_col10[p]) {
+            FastColArgs a{};
+            a.src = cur_src;
+            a.dst = scratch;
+            a.src_array_words = cur_src_words;
+            a.dst_array_words = array_words;
+            a.w = w;
+            a.inner_words = inner_words;
+            a.n_col_tiles = (u32)(inner_words / kFastCols);
+            a.n_outer = n_outer;
+            a.n_in_elems = cur_n_in;
+            a.t1 = t1;
+            a.tw_full = tw_full;
+            a.tw = tw;
+            a.log_b = log_b;
+            a.tw_scalar = tw_scalar;
+            a.pre = cur_pre;
+            u64 grid = batch * n_outer * a.n_col_tiles;
+            if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+            if (inverse)
+                TF21_TRY(launch_fast(ntt1024_col_kernel<true>, (unsigned)grid, a, st));
+            else
+                TF21_TRY(launch_fast(ntt1024_col_kernel<false>, (unsigned)grid, a, st));
+        } else {
+            SmallColArgs a{};
+            a.src = cur_src;
+            a.dst = scratch;
+            a.src_array_words = cur_src_words;
+            a.dst_array_words = array_words;
+            a.w = w;
+            a.inner_words = inner_words;
+            a.n_outer = n_outer;
+            a.n_in_elems = cur_n_in;
+            a.tw_full = tw_full;
+            a.tw = tw;
+            a.tw_scalar = tw_scalar;
+            a.pre = cur_pre;
+            u64 grid = batch * n_outer * (inner_words / 128);
+            if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+            if (inverse)
+                TF21_TRY(launch_small<true>(lp, (unsigned)grid, a, st));
+            else
+                TF21_TRY(launch_small<false>(lp, (unsigned)grid, a, st));
+        }
+        consumed += lp;
+        cur_src = scratch;
+        cur_src_words = array_words;
+        cur_n_in = n;
+        cur_pre = ScaleTab{nullptr, nullptr, 0};
+    }
+
+    FastRowArgs a{};
+    a.src = cur_src;
+    a.dst = dst;
+    a.array_words = array_words;
+    a.w = w;
+    a.n1 = 1u << lead[0];
+    a.n2 = n_lead > 1 ? 1u << lead[1] : 1u;
+    a.n3 = n_lead > 2 ? 1u << lead[2] : 1u;
+    const u64 rows = n >> 10;
+    a.n_tiles = (u32)(rows * w / kFastCols);
+    a.t1 = t1;
+    a.post_scalar = post_scalar;
+    a.post = post;
+    u64 grid = batch * a.n_tiles;
+    if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+    if (inverse) return launch_fast(ntt1024_row_kernel<true>, (unsigned)grid, a, st);
+    return launch_fast(ntt1024_row_kernel<false>, (unsigned)grid, a, st);
 }
 
 }  // namespace tf21
