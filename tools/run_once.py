@@ -13,6 +13,16 @@ if what == "ntt20":
     x = torch.randint(0, 2**63 - 1, (cols << 20,), dtype=torch.int64, device=cuda)
     for _ in range(reps):
         dev.ntt_(x, 1 << 20, 1, False)
+elif what == "ntt16":
+    x = torch.randint(0, 2**63 - 1, (1024 << 16,), dtype=torch.int64, device=cuda)
+    for _ in range(reps):
+        dev.ntt_(x, 1 << 16, 1, False)
+elif what == "lde26":
+    vals = torch.randint(0, 2**63 - 1, (3 << 22,), dtype=torch.int64, device=cuda)
+    out = torch.zeros(3 << 26, dtype=torch.int64, device=cuda)
+    g = tf.BFieldElement.generator()
+    for _ in range(reps):
+        dev.coset_lde(vals, 3, g, 1 << 26, g, out)
 elif what == "ntt10":
     x = torch.randint(0, 2**63 - 1, (16384 << 10,), dtype=torch.int64, device=cuda)
     for _ in range(reps):

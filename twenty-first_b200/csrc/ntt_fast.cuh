@@ -211,7 +211,7 @@ struct FastRowArgs {
 // o' + rows * i_k with o' = i_1 + n1 (i_2 + n2 i_3) (digit reversal of the row index).  A CTA takes 8
 // consecutive word-columns tc = o' * w + c of the output; a warp loads its row directly (stride w),
 // the transposed store goes through shared memory; canonical on store.
-template <bool INV>
+template <bool INV, u32 W>
 __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_row_kernel(const FastRowArgs a) {
     extern __shared__ u64 smem[];
     u64 *tile = smem;
@@ -222,14 +222,14 @@ __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_row_kernel(const Fast
     const u32 rows = a.n1 * a.n2 * a.n3;
     {
         const u32 tc = tc0 + warp;
-        const u32 op = tc / a.w, c = tc - op * a.w;
+        const u32 op = tc / W, c = tc - op * W;
         const u32 i1 = op % a.n1, r23 = op / a.n1;
         const u32 i2 = r23 % a.n2, i3 = r23 / a.n2;
         const u64 rho = ((u64)i1 * a.n2 + i2) * a.n3 + i3;
-        const u64 *row = a.src + (u64)b * a.array_words + rho * 1024 * a.w + c;
+        const u64 *row = a.src + (u64)b * a.array_words + rho * 1024 * W + c;
         u64 v[32];
 #pragma unroll
-        for (int aa = 0; aa < 32; aa++) v[aa] = row[(u64)(32 * aa + lane) * a.w];
+        for (int aa = 0; aa < 32; aa++) v[aa] = row[(u64)(32 * aa + lane) * W];
         dft1024_warp<INV>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane);
     }
     __syncthreads();
@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_row_kernel(const Fast
         const u32 tc = tc0 + c8;
         u64 *dst = a.dst + (u64)b * a.array_words + tc;
         const u64 *tl = tile + c8 * kFastS;
-        const u64 ostride = (u64)rows * a.w;
-        const u64 op = tc / a.w;  // element index = op + rows * r
+        const u64 ostride = (u64)rows * W;
+        const u64 op = tc / W;  // element index = op + rows * r
 #pragma unroll 8
         for (u32 it = 0; it < 32; it++) {
             const u32 r = warp * 128 + it * 4 + rsub;
@@ -460,20 +460,21 @@ inline int get_tw_small(DeviceTables &t, int dev, unsigned log_b, unsigned log_n
 }
 
 template <typename K, typename A>
-inline int launch_fast(K kernel, unsigned grid, const A &args, cudaStream_t st) {
-    TF21_LAUNCH(kernel, grid, kFastThreads, kFastSmem, st, args);
+inline int launch_fast_named(const char *name, K kernel, unsigned grid, const A &args, cudaStream_t st) {
+    TF21_LAUNCH_NAMED(name, kernel, grid, kFastThreads, kFastSmem, st, args);
     return 0;
 }
+#define launch_fast(kernel, grid, args, st) launch_fast_named(#kernel, kernel, grid, args, st)
 
 template <bool INV>
 inline int launch_small(u32 a_log, unsigned grid, const SmallColArgs &args, cudaStream_t st) {
     switch (a_log) {
-        case 1: TF21_LAUNCH((ntt_small_col_kernel<INV, 1>), grid, 128, 0, st, args); break;
-        case 2: TF21_LAUNCH((ntt_small_col_kernel<INV, 2>), grid, 128, 0, st, args); break;
-        case 3: TF21_LAUNCH((ntt_small_col_kernel<INV, 3>), grid, 128, 0, st, args); break;
-        case 4: TF21_LAUNCH((ntt_small_col_kernel<INV, 4>), grid, 128, 0, st, args); break;
-        case 5: TF21_LAUNCH((ntt_small_col_kernel<INV, 5>), grid, 128, 0, st, args); break;
-        case 6: TF21_LAUNCH((ntt_small_col_kernel<INV, 6>), grid, 128, 0, st, args); break;
+        case 1: TF21_LAUNCH_NAMED("ntt_small_col_kernel", (ntt_small_col_kernel<INV, 1>), grid, 128, 0, st, args); break;
+        case 2: TF21_LAUNCH_NAMED("ntt_small_col_kernel", (ntt_small_col_kernel<INV, 2>), grid, 128, 0, st, args); break;
+        case 3: TF21_LAUNCH_NAMED("ntt_small_col_kernel", (ntt_small_col_kernel<INV, 3>), grid, 128, 0, st, args); break;
+        case 4: TF21_LAUNCH_NAMED("ntt_small_col_kernel", (ntt_small_col_kernel<INV, 4>), grid, 128, 0, st, args); break;
+        case 5: TF21_LAUNCH_NAMED("ntt_small_col_kernel", (ntt_small_col_kernel<INV, 5>), grid, 128, 0, st, args); break;
+        case 6: TF21_LAUNCH_NAMED("ntt_small_col_kernel", (ntt_small_col_kernel<INV, 6>), grid, 128, 0, st, args); break;
         default: return TF21_E_BAD_ARG;
     }
     return 0;
@@ -598,9 +599,9 @@ inline int ntt_run_generic(DeviceTables &tabs, const u64 *src, u64 n_in, u64 *ds
 // table lookups lock g_mutex internally.
 //
 // Pass plan for n >= 2^13 (register-resident kernels only):
-//   [ one or two "small" column passes of 2^a <= 64 points ]  [ a 1024-point column pass if log2 n >= 20 ]
+//   [ one or two "small" column passes of 2^a <= 32 points ]  [ a 1024-point column pass if log2 n >= 20 ]
 //   [ the 1024-point transposing row pass ]
-// e.g. 2^20 = 1024 x 1024, 2^22 = 4 x 1024 x 1024, 2^26 = 64 x 1024 x 1024, 2^16 = 64 x 1024.
+// e.g. 2^20 = 1024 x 1024, 2^22 = 4 x 1024 x 1024, 2^26 = 8 x 8 x 1024 x 1024, 2^16 = 8 x 8 x 1024.
 inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *dst, u64 n, u32 w, u64 batch,
                    int inverse, ScaleTab pre, ScaleTab post, u64 post_scalar, u64 *scratch, cudaStream_t st) {
     const u32 log_n = ilog2_u64(n);
@@ -639,7 +640,7 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         u32 rem = log_n - 10;
         const bool has_col = rem >= 10;
         if (has_col) rem -= 10;
-        if (rem > 6) {
+        if (rem > 5) {  // 64-point columns per thread do not pay: ~200 KB of straight-line code, 196 registers
             lead[n_lead++] = (rem + 1) / 2;
             lead[n_lead++] = rem / 2;
         } else if (rem > 0) {
@@ -750,8 +751,12 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     a.post = post;
     u64 grid = batch * a.n_tiles;
     if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-    if (inverse) return launch_fast(ntt1024_row_kernel<true>, (unsigned)grid, a, st);
-    return launch_fast(ntt1024_row_kernel<false>, (unsigned)grid, a, st);
+    if (w == 1) {
+        if (inverse) return launch_fast_named("ntt1024_row_kernel", ntt1024_row_kernel<true, 1>, (unsigned)grid, a, st);
+        return launch_fast_named("ntt1024_row_kernel", ntt1024_row_kernel<false, 1>, (unsigned)grid, a, st);
+    }
+    if (inverse) return launch_fast_named("ntt1024_row_kernel", ntt1024_row_kernel<true, 3>, (unsigned)grid, a, st);
+    return launch_fast_named("ntt1024_row_kernel", ntt1024_row_kernel<false, 3>, (unsigned)grid, a, st);
 }
 
 }  // namespace tf21

@@ -65,17 +65,19 @@ inline void prof_end(cudaStream_t st, ProfRec *r) {
 }
 
 // every kernel launch of the library goes through this so bench.py can report gpu_launches
-#define TF21_LAUNCH(kernel, grid, block, smem, stream, ...)                     \
+#define TF21_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)          \
     do {                                                                        \
         tf21::ProfRec _pr;                                                      \
         const bool _prof = tf21::g_prof_enabled.load(std::memory_order_relaxed); \
-        if (_prof) tf21::prof_begin(#kernel, (stream), &_pr);                   \
+        if (_prof) tf21::prof_begin((name), (stream), &_pr);                    \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
         if (_prof) tf21::prof_end((stream), &_pr);                              \
         tf21::g_launches.fetch_add(1, std::memory_order_relaxed);               \
         cudaError_t _e = cudaGetLastError();                                    \
-        if (_e != cudaSuccess) return tf21::cuda_fail(_e, #kernel, __LINE__);   \
+        if (_e != cudaSuccess) return tf21::cuda_fail(_e, (name), __LINE__);    \
     } while (0)
+#define TF21_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    TF21_LAUNCH_NAMED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
 
 inline unsigned ilog2_u64(uint64_t n) { return 63u - (unsigned)__builtin_clzll(n); }
 

@@ -48,8 +48,10 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
                                        (int)t.smem_optin));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         t.constants_ready = true;
