@@ -89,6 +89,8 @@ def cpu_reference_leg(steps: int, warmup: int, sample_cols: int | None, merkle_l
     import oracle
 
     o = oracle.get(native=True)
+    # all host threads, like rayon's default pool; torchrun exports OMP_NUM_THREADS=1, undo that here
+    o.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cores = o.num_threads()
     n = 1 << LOG2N
     cols = sample_cols or max(cores, 8)

@@ -246,6 +246,9 @@ class Oracle:
     def num_threads(self) -> int:
         return self.lib.oracle_num_threads()
 
+    def set_num_threads(self, n: int) -> None:
+        self.lib.oracle_set_num_threads(int(n))
+
 
 _default = None
 

@@ -616,3 +616,12 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+
+/* rayon sizes its pool from the machine, not from OMP_NUM_THREADS (which torchrun sets to 1) */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -59,6 +59,7 @@ uint64_t oracle_bfe_primitive_root_of_unity(uint64_t n);
 void oracle_bfe_new_array(uint64_t *x, uint64_t n);
 void oracle_bfe_value_array(uint64_t *x, uint64_t n);
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtf21.so")
+LIB_PATH = os.environ.get("TF21_LIB") or os.path.join(_HERE, "libtf21.so")  # TF21_LIB: developer A/B builds
 
 OK = 0
 E_LEN_NOT_POW2 = -1

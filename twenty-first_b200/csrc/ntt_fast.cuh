@@ -65,9 +65,9 @@ __device__ __forceinline__ void dft_pow2(u64 (&v)[1 << A]) {
                 const u64 u = v[iu];
                 if (!neg) {
                     v[iu] = gl_addl(u, t);
-                    v[ib] = gl_sub(u, t);
+                    v[ib] = gl_subl(u, t);
                 } else {
-                    v[iu] = gl_sub(u, t);
+                    v[iu] = gl_subl(u, t);
                     v[ib] = gl_addl(u, t);
                 }
             }

@@ -265,19 +265,59 @@ struct DevBuf {
     }
 };
 
+// Host-slice NTT.  A batch is cut into chunks of whole arrays that go H2D -> kernels -> D2H on three
+// streams, so the two PCIe directions and the compute overlap (the copies dominate: PCIe is ~100x
+// slower than HBM).  Pinned host memory gets the full benefit; pageable memory is still correct.
 static int host_ntt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch, int inverse) {
     TF21_TRY(check_ntt_len(n, width));
     if (n <= 1 || batch == 0) return 0;
     if (!data) return TF21_E_BAD_ARG;
     DeviceTables *t;
     TF21_TRY(get_tables(&t));
-    u64 words = n * width * batch;
-    DevBuf buf;
-    TF21_TRY(buf.alloc(words));
-    TF21_CUDA(cudaMemcpy(buf.p, data, words * sizeof(u64), cudaMemcpyHostToDevice));
-    TF21_TRY(tf21_ntt_dev(buf.p, n, width, batch, inverse, nullptr));
-    TF21_CUDA(cudaMemcpy(data, buf.p, words * sizeof(u64), cudaMemcpyDeviceToHost));
-    return 0;
+    const u64 array_words = n * width;
+    const u64 kChunkBytes = 64ull << 20;
+    u64 chunk_arrays = kChunkBytes / (array_words * sizeof(u64));
+    if (chunk_arrays < 1) chunk_arrays = 1;
+    if (chunk_arrays > batch) chunk_arrays = batch;
+    const u64 n_chunks = (batch + chunk_arrays - 1) / chunk_arrays;
+    const int n_streams = (int)(n_chunks < 3 ? n_chunks : 3);
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    u64 *bufs[3] = {nullptr, nullptr, nullptr};
+    int rc = 0;
+    auto cleanup = [&]() {
+        for (int i = 0; i < n_streams; i++) {
+            if (streams[i]) {
+                if (bufs[i]) cudaFreeAsync(bufs[i], streams[i]);
+                cudaStreamSynchronize(streams[i]);
+                cudaStreamDestroy(streams[i]);
+            }
+        }
+    };
+    for (int i = 0; i < n_streams && rc == 0; i++) {
+        if (cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMallocAsync((void **)&bufs[i], chunk_arrays * array_words * sizeof(u64), streams[i]) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "host_ntt staging", __LINE__);
+    }
+    for (u64 c = 0; c < n_chunks && rc == 0; c++) {
+        const int si = (int)(c % (u64)n_streams);
+        const u64 a0 = c * chunk_arrays;
+        const u64 cnt = (a0 + chunk_arrays <= batch) ? chunk_arrays : batch - a0;
+        const u64 bytes = cnt * array_words * sizeof(u64);
+        uint64_t *h = data + a0 * array_words;
+        if (cudaMemcpyAsync(bufs[si], h, bytes, cudaMemcpyHostToDevice, streams[si]) != cudaSuccess) {
+            rc = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync H2D", __LINE__);
+            break;
+        }
+        rc = tf21_ntt_dev(bufs[si], n, width, cnt, inverse, (tf21_stream_t)streams[si]);
+        if (rc) break;
+        if (cudaMemcpyAsync(h, bufs[si], bytes, cudaMemcpyDeviceToHost, streams[si]) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync D2H", __LINE__);
+    }
+    for (int i = 0; i < n_streams && rc == 0; i++)
+        if (streams[i] && cudaStreamSynchronize(streams[i]) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "cudaStreamSynchronize", __LINE__);
+    cleanup();
+    return rc;
 }
 
 int tf21_ntt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch) { return host_ntt(data, n, width, batch, 0); }

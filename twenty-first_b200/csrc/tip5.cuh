@@ -18,6 +18,12 @@
 #pragma once
 #include "field.cuh"
 
+#ifndef TIP5_MDS_ORDER
+#define TIP5_MDS_ORDER 0
+#endif
+#ifndef TIP5_MIN_BLOCKS
+#define TIP5_MIN_BLOCKS 1
+#endif
 #define TIP5_STATE 16
 #define TIP5_RATE 10
 #define TIP5_ROUNDS 5
@@ -81,6 +87,33 @@ __device__ __forceinline__ void tip5_permutation(u64 (&s)[TIP5_STATE], const uin
             dl[j] = __hiloint2double(0x43300000, (int)(u32)s[j]) - kBias;
             dh[j] = __hiloint2double(0x43300000, (int)(u32)(s[j] >> 32)) - kBias;
         }
+#if TIP5_MDS_ORDER == 1
+        // j-outer: 32 independent accumulator chains (maximum ILP on the FP64 pipe)
+        double al[TIP5_STATE], ah[TIP5_STATE];
+#pragma unroll
+        for (int i = 0; i < TIP5_STATE; i++) {
+            al[i] = c_tip5_rc_lo[r * TIP5_STATE + i];
+            ah[i] = c_tip5_rc_hi[r * TIP5_STATE + i];
+        }
+#pragma unroll
+        for (int j = 0; j < TIP5_STATE; j++) {
+#pragma unroll
+            for (int i = 0; i < TIP5_STATE; i++) {
+                const double m = (double)TIP5_MDS((i - j) & 15);
+                al[i] = fma(m, dl[j], al[i]);
+                ah[i] = fma(m, dh[j], ah[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TIP5_STATE; i++) {
+            const u64 acc_lo = (u64)__double_as_longlong(al[i] + kBias) & 0x000FFFFFFFFFFFFFull;
+            const u64 acc_hi = (u64)__double_as_longlong(ah[i] + kBias) & 0x000FFFFFFFFFFFFFull;
+            u64 x0 = acc_lo + (acc_hi << 32);
+            u32 x1 = (u32)(acc_hi >> 32) + (x0 < acc_lo ? 1u : 0u);
+            u64 v = gl_reduce96(x0, x1);
+            s[i] = (i < 4) ? gl_canon(v) : v;
+        }
+#else
 #pragma unroll
         for (int i = 0; i < TIP5_STATE; i++) {
             double al = c_tip5_rc_lo[r * TIP5_STATE + i];
@@ -100,6 +133,7 @@ __device__ __forceinline__ void tip5_permutation(u64 (&s)[TIP5_STATE], const uin
             u64 v = gl_reduce96(x0, x1);
             s[i] = (i < 4) ? gl_canon(v) : v;
         }
+#endif
     }
 }
 

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kTip5Threads) tip5_permute_kernel(u64 *__restr
 }
 
 // Tip5::hash_10 / hash_pair over a batch (tip5/mod.rs:559-586): state = in[0..10) | ONE x 6
-__global__ void __launch_bounds__(kTip5Threads)
+__global__ void __launch_bounds__(kTip5Threads, TIP5_MIN_BLOCKS)
     tip5_hash10_kernel(const u64 *__restrict__ in, u64 count, u64 *__restrict__ out) {
     __shared__ uint8_t s_lut[256];
     tip5_load_lut(s_lut);
