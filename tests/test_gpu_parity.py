@@ -244,7 +244,8 @@ def test_coset_evaluate_degree_rules(tf, oracle):
     assert not z.any()
 
 
-@pytest.mark.parametrize("log_in,log_out,width", [(0, 0, 1), (0, 4, 3), (4, 4, 1), (6, 10, 3), (10, 14, 1), (12, 16, 3), (16, 20, 3), (18, 22, 3), (13, 13, 1)])
+@pytest.mark.parametrize("log_in,log_out,width", [(0, 0, 1), (0, 4, 3), (4, 4, 1), (6, 10, 3), (10, 14, 1), (12, 16, 3), (16, 20, 3), (18, 22, 3), (13, 13, 1),
+                                                       (13, 16, 1), (11, 16, 3), (17, 21, 1), (14, 23, 1), (12, 18, 3), (13, 19, 1)])
 def test_coset_lde_matches_oracle(tf, oracle, log_in, log_out, width):
     n_in, n_out = 1 << log_in, 1 << log_out
     values = rnd(500 + log_in + log_out, n_in * width)
@@ -378,3 +379,16 @@ def test_merkle_sharded_assembly_equals_single_tree(tf, oracle):
     torch.cuda.synchronize()
     got = global_nodes.cpu().numpy().view(np.uint64)
     assert np.array_equal(got, want)
+
+
+def test_coset_lde_full_size_config3(tf, oracle):
+    """BASELINE configs[3]: 2^22 -> 2^26 XFieldElement, offsets 7 -> 7, every output word against the oracle."""
+    n_in, n_out = 1 << 22, 1 << 26
+    values = rnd(0x210003, 3 * n_in)
+    g = tf.BFieldElement.generator()
+    rc, coeffs = oracle.coset_interpolate(values, 3, g)
+    assert rc == 0
+    rc, want = oracle.coset_evaluate(coeffs, 3, g, n_out)
+    assert rc == 0
+    got = tf.Polynomial.coset_lde(values.reshape(n_in, 3), g, n_out, g)
+    assert np.array_equal(got.reshape(-1), want)

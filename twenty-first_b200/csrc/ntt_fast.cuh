@@ -319,6 +319,74 @@ __global__ void __launch_bounds__(128) ntt_small_col_kernel(const SmallColArgs a
     }
 }
 
+// Pruned column pass for zero-extended inputs (the `resize(order, ZERO)` of fast_coset_evaluate,
+// polynomial.rs:1396-1397): only the first NZ = 2^LNZ rows of a 2^A-point column can be non-zero, so
+// with M = 2^A / NZ and k = M c + d:  X[M c + d] = sum_{a < NZ} (x_a w^(a d)) w_NZ^(a c)  -- for every d one
+// NZ-point DFT of shift-twiddled inputs.  Reads NZ rows, writes 2^A rows, keeps 2 NZ values live.
+template <int A, int LNZ>
+__global__ void __launch_bounds__(128) ntt_small_col_pruned_kernel(const SmallColArgs a) {
+    constexpr int NP = 1 << A, NZ = 1 << LNZ, M = NP / NZ;
+    constexpr int EU = (39 << (6 - A)) % 192;
+    const u64 gid = (u64)blockIdx.x * 128 + threadIdx.x;
+    const u64 q = gid % a.inner_words;
+    const u64 rest = gid / a.inner_words;
+    const u32 o = (u32)(rest % a.n_outer);
+    const u64 b = rest / a.n_outer;
+    const u64 inner_elems = a.inner_words / a.w;
+    const u64 jcol = q / a.w;
+    const u64 off = (u64)o * NP * a.inner_words + q;
+    const u64 *src = a.src + b * a.src_array_words + off;
+    u64 x[NZ];
+#pragma unroll
+    for (int r = 0; r < NZ; r++) {
+        const u64 j = ((u64)o * NP + r) * inner_elems + jcol;
+        u64 v = 0;
+        if (j < a.n_in_elems) {
+            v = src[(u64)r * a.inner_words];
+            if (a.pre.lo) v = gl_mul(v, scale_factor_l(a.pre, j));
+        }
+        x[r] = v;
+    }
+    u64 *dst = a.dst + b * a.dst_array_words + off;
+    // inter-pass twiddle omega_B^(i jcol): table column, or g^i = g^d (g^M)^c from g = omega_B^jcol
+    const u64 *tcol = a.tw_full ? a.tw_full + jcol : nullptr;
+    u64 g = 0, gM = 0, gd = 1;
+    if (!tcol) {
+        g = scale_factor_l(a.tw, jcol);
+        gM = g;
+#pragma unroll
+        for (int k = 0; k < A - LNZ; k++) gM = gl_mul(gM, gM);
+    }
+#pragma unroll
+    for (int d = 0; d < M; d++) {
+        u64 z[NZ];
+#pragma unroll
+        for (int r = 0; r < NZ; r++) {
+            const int E = (EU * r * d) % 192;
+            const bool neg = E >= 96;
+            const int S = neg ? E - 96 : E;
+            u64 t = (S == 0) ? x[r] : gl_shlc(x[r], S);
+            if (neg) t = gl_sub(0ull, gl_canonw(t));
+            z[r] = t;
+        }
+        dft_pow2<false, LNZ>(z);
+        u64 tc = gd;
+#pragma unroll
+        for (int c = 0; c < NZ; c++) {
+            const int i = M * c + d;
+            u64 v = z[brev_bits(c, LNZ)];
+            if (tcol) {
+                v = gl_mul(v, __ldg(tcol + (u64)i * inner_elems));
+            } else {
+                if (i != 0) v = gl_mul(v, tc);
+                if (c + 1 < NZ) tc = gl_mul(tc, gM);
+            }
+            dst[(u64)i * a.inner_words] = v;
+        }
+        if (!tcol && d + 1 < M) gd = gl_mul(gd, g);
+    }
+}
+
 struct FastSingleArgs {
     const u64 *src;
     u64 *dst;
@@ -478,6 +546,32 @@ inline int launch_small(u32 a_log, unsigned grid, const SmallColArgs &args, cuda
         default: return TF21_E_BAD_ARG;
     }
     return 0;
+}
+
+inline int launch_small_pruned(u32 a_log, u32 lnz, unsigned grid, const SmallColArgs &args, cudaStream_t st) {
+#define TF21_PRUNED_CASE(A_, L_)                                                                          \
+    if (a_log == (A_) && lnz == (L_)) {                                                                   \
+        TF21_LAUNCH_NAMED("ntt_small_col_pruned_kernel", (ntt_small_col_pruned_kernel<A_, L_>), grid, 128, 0, st, \
+                          args);                                                                          \
+        return 0;                                                                                         \
+    }
+    TF21_PRUNED_CASE(1, 0)
+    TF21_PRUNED_CASE(2, 0) TF21_PRUNED_CASE(2, 1)
+    TF21_PRUNED_CASE(3, 0) TF21_PRUNED_CASE(3, 1) TF21_PRUNED_CASE(3, 2)
+    TF21_PRUNED_CASE(4, 0) TF21_PRUNED_CASE(4, 1) TF21_PRUNED_CASE(4, 2) TF21_PRUNED_CASE(4, 3)
+    TF21_PRUNED_CASE(5, 0) TF21_PRUNED_CASE(5, 1) TF21_PRUNED_CASE(5, 2) TF21_PRUNED_CASE(5, 3)
+    TF21_PRUNED_CASE(6, 0) TF21_PRUNED_CASE(6, 1) TF21_PRUNED_CASE(6, 2) TF21_PRUNED_CASE(6, 3)
+#undef TF21_PRUNED_CASE
+    return TF21_E_BAD_ARG;
+}
+
+// number of leading rows of a 2^a_log-point first pass that can be non-zero, as a log2 (rounded up)
+inline u32 nonzero_rows_log(u64 n_in, u64 inner_elems, u32 a_log) {
+    u64 rows = (n_in + inner_elems - 1) / inner_elems;
+    if (rows < 1) rows = 1;
+    u32 l = 0;
+    while (((u64)1 << l) < rows) l++;
+    return l > a_log ? a_log : l;
 }
 
 // generic (shared-memory radix-2) path: sizes below 2^13 and width-3 single passes
@@ -640,7 +734,13 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         u32 rem = log_n - 10;
         const bool has_col = rem >= 10;
         if (has_col) rem -= 10;
-        if (rem > 5) {  // 64-point columns per thread do not pay: ~200 KB of straight-line code, 196 registers
+        // zero-extended input (coset evaluate / LDE): one pruned pass over all the small bits reads only the
+        // non-zero rows and replaces two full passes
+        const bool prune_all = !inverse && n_in < n && rem >= 1 && rem <= 6 &&
+                               nonzero_rows_log(n_in, n >> rem, rem) <= 3 && nonzero_rows_log(n_in, n >> rem, rem) < rem;
+        if (prune_all) {
+            lead[n_lead++] = rem;
+        } else if (rem > 5) {  // 64-point columns per thread do not pay: ~200 KB of straight-line code, 196 registers
             lead[n_lead++] = (rem + 1) / 2;
             lead[n_lead++] = rem / 2;
         } else if (rem > 0) {
@@ -724,7 +824,10 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
             a.pre = cur_pre;
             u64 grid = batch * n_outer * (inner_words / 128);
             if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-            if (inverse)
+            const u32 lnz = (p == 0 && !inverse) ? nonzero_rows_log(cur_n_in, inner_words / w, lp) : lp;
+            if (lnz < lp && lnz <= 3)
+                TF21_TRY(launch_small_pruned(lp, lnz, (unsigned)grid, a, st));
+            else if (inverse)
                 TF21_TRY(launch_small<true>(lp, (unsigned)grid, a, st));
             else
                 TF21_TRY(launch_small<false>(lp, (unsigned)grid, a, st));
