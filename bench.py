@@ -62,7 +62,7 @@ class ClockSampler:
                     self.samples.append(parts)
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05)
 
     def __enter__(self):
         self.thread.start()
@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--cpu-cols", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lde", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -255,6 +256,21 @@ def main():
             agg[name] = (tot + ms, cnt + 1)
         return agg
 
+    # DRAM traffic per launch of the dominant kernels, from the committed `ncu --set full` capture of the
+    # same shapes (profiles/r01_ncu_traffic.json, written by tools/ncu_traffic.py); null if absent
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_db = json.load(f)
+
+    def traffic_of(kernel_name, shape_key):
+        e = traffic_db.get(shape_key, {})
+        for k, v in e.items():
+            if k.split("<")[0] == kernel_name.split("<")[0]:
+                return v
+        return None
+
     ntt_agg = by_kernel(ntt_prof)
     ntt_kernel_ms = sum(t for t, _ in ntt_agg.values())
     # one batched transform (all its pass launches) is the roofline unit: 2*8*n bytes per column
@@ -267,6 +283,24 @@ def main():
     merkle_kernel_ms = sum(t for t, _ in merkle_agg.values()) / args.steps
     merkle_alg_bytes = 80 * n_leafs
     merkle_achieved = merkle_alg_bytes / (merkle_kernel_ms * 1e-3) / 1e9
+
+    # ---- secondary workload: BASELINE configs[3], coset LDE 2^22 -> 2^26 XFieldElement (rank 0 timing) ----
+    lde = None
+    if not args.no_lde:
+        li, lo = 22, 26
+        vals = torch.randint(0, 2**63 - 1, (3 << li,), dtype=torch.int64, device=cuda, generator=gen)
+        out = torch.zeros(3 << lo, dtype=torch.int64, device=cuda)
+        g7 = tf.BFieldElement.generator()
+        for _ in range(2):
+            dev.coset_lde(vals, 3, g7, 1 << lo, g7, out)
+        lde_steps = max(1, min(args.steps, 3))
+        lde_ms = timed(lambda: dev.coset_lde(vals, 3, g7, 1 << lo, g7, out), lde_steps) / lde_steps
+        lde_bytes = 24 * ((1 << li) + (1 << lo))
+        lde = {"workload": "coset LDE 2^22 -> 2^26 XFieldElement per GPU (BASELINE configs[3])", "ms": lde_ms,
+               "algorithmic_bytes": lde_bytes,
+               "roofline": {"bound": "hbm", "achieved": lde_bytes / (lde_ms * 1e-3) / 1e9, "peak": peak_gbs,
+                            "unit": "GB/s", "frac": lde_bytes / (lde_ms * 1e-3) / 1e9 / peak_gbs}}
+        del vals, out
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ------------------------
     e2e = None
@@ -307,7 +341,12 @@ def main():
                        "columns_per_gpu": cols, "log2_n": LOG2N, "l2_policy": "inputs (2 GiB per GPU) larger than L2",
                        "transforms_per_step": transforms_per_step},
             "roofline": {"bound": "hbm", "achieved": ntt_achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": ntt_achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "frac": ntt_achieved / peak_gbs,
+                         "traffic": (lambda a, b: (a + b) if (a and b) else None)(
+                             traffic_of("ntt1024_col_kernel", f"ntt20_cols{cols}"),
+                             traffic_of("ntt1024_row_kernel", f"ntt20_cols{cols}")),
+                         "traffic_note": "dram read+write bytes of one col-pass launch + one row-pass launch (ncu)",
+                         "peak_source": peak_src,
                          "kernel": "one batched 2^20 transform = " + " + ".join(sorted(ntt_agg)),
                          "launches_per_transform": launches_per_transform,
                          "algorithmic_bytes_per_launch_group": ntt_alg_bytes,
@@ -317,10 +356,12 @@ def main():
             "merkle": {"value": leaves_per_s, "unit": "leaves/s", "ms_per_step": merkle_ms / args.steps,
                        "leaves_per_gpu": n_leafs,
                        "roofline": {"bound": "hbm", "achieved": merkle_achieved, "peak": peak_gbs, "unit": "GB/s",
-                                    "frac": merkle_achieved / peak_gbs, "traffic": None,
+                                    "frac": merkle_achieved / peak_gbs,
+                                    "traffic": traffic_of("tip5_hash10_kernel", f"merkle{args.merkle_log2}"),
+                                    "traffic_note": "dram bytes of the leaf-level tip5_hash10_kernel launch (ncu)",
                                     "algorithmic_bytes": merkle_alg_bytes, "kernel_ms": merkle_kernel_ms,
                                     "per_kernel_ms_total": {k: t / args.steps for k, (t, c) in merkle_agg.items()}}},
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clock_summary,
+            "lde": lde, "cpu_baseline": cpu, "e2e": e2e, "clocks": clock_summary,
             "gpu_launches": int(l2 - l0), "gpu_launches_ntt": int(l1 - l0),
         }
         print(json.dumps(line), flush=True)
