@@ -57,6 +57,8 @@ extern "C" {
     pub fn tf21_tip5_hash_10_dev(input: *const u64, count: u64, out: *mut u64, s: tf21_stream_t) -> c_int;
     pub fn tf21_tip5_hash_rows_dev(rows: *const u64, row_len: u64, n_rows: u64, out: *mut u64,
                                    s: tf21_stream_t) -> c_int;
+    pub fn tf21_tip5_hash_columns_dev(cols: *const u64, n_rows: u64, n_cols: u64, col_stride_words: u64,
+                                      out: *mut u64, s: tf21_stream_t) -> c_int;
 
     pub fn tf21_merkle_build(leafs: *const u64, n_leafs: u64, nodes_out: *mut u64) -> c_int;
     pub fn tf21_merkle_root(leafs: *const u64, n_leafs: u64, root_out: *mut u64) -> c_int;

@@ -119,6 +119,12 @@ int tf21_tip5_permute_dev(uint64_t *d_states, uint64_t count, tf21_stream_t stre
 int tf21_tip5_hash_10_dev(const uint64_t *d_in, uint64_t count, uint64_t *d_out, tf21_stream_t stream);
 int tf21_tip5_hash_rows_dev(const uint64_t *d_rows, uint64_t row_len, uint64_t n_rows,
                             uint64_t *d_out, tf21_stream_t stream);
+/* Same for column-major data (a batch of NTT codewords as tf21_ntt_dev leaves them): digest i =
+ * hash_varlen(col_0[i], col_1[i], .., col_{n_cols-1}[i]) with col_c = d_cols + c * col_stride_words.
+ * This is the step between the NTT codewords and MerkleTree::par_new in the crate's callers
+ * (SURVEY.md 8f-1); loads are coalesced across rows.                                            */
+int tf21_tip5_hash_columns_dev(const uint64_t *d_cols, uint64_t n_rows, uint64_t n_cols,
+                               uint64_t col_stride_words, uint64_t *d_out, tf21_stream_t stream);
 
 /* ---- Merkle tree (merkle_tree.rs:149-222, 299-364, 393-429) -------------------------------- */
 /* nodes_out has 2*n_leafs digests: nodes[0] = 0, nodes[1] = root,

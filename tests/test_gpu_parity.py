@@ -392,3 +392,58 @@ def test_coset_lde_full_size_config3(tf, oracle):
     assert rc == 0
     got = tf.Polynomial.coset_lde(values.reshape(n_in, 3), g, n_out, g)
     assert np.array_equal(got.reshape(-1), want)
+
+
+def test_tip5_hash_columns_matches_row_hashing(tf, oracle):
+    """column-major codewords -> leaf digests: equals hash_varlen of the transposed rows"""
+    import torch
+
+    dev = importlib.import_module("twenty-first_b200.device")
+    cuda = torch.device("cuda:0")
+    for n_rows, n_cols in ((1, 1), (257, 7), (1024, 10), (4096, 33)):
+        cols = rnd(0xC0 + n_cols, n_rows * n_cols).reshape(n_cols, n_rows)
+        d_cols = torch.from_numpy(cols.view(np.int64)).to(cuda)
+        out = torch.zeros(5 * n_rows, dtype=torch.int64, device=cuda)
+        dev.tip5_hash_columns(d_cols, n_rows, n_cols, out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(np.uint64).reshape(n_rows, 5)
+        rows = np.ascontiguousarray(cols.T)
+        for r in range(0, n_rows, max(1, n_rows // 13)):
+            assert np.array_equal(got[r], oracle.hash_varlen(np.ascontiguousarray(rows[r])))
+        assert np.array_equal(got, tf.Tip5.hash_rows(rows))
+
+
+def test_concurrent_callers_are_thread_safe(tf, oracle):
+    """The Rust items are callable from any rayon worker (ntt.rs:71 OnceLock tables): hammer the C ABI
+    from several host threads at once (ctypes releases the GIL) with different sizes."""
+    import threading
+
+    jobs = [(10, 1), (13, 1), (16, 1), (12, 3), (20, 1), (14, 3), (17, 1), (11, 1)]
+    inputs = [rnd(0xAB00 + i, (1 << l) * w) for i, (l, w) in enumerate(jobs)]
+    wants = []
+    for (l, w), x in zip(jobs, inputs):
+        y = x.copy()
+        oracle.ntt(y, w)
+        wants.append(y)
+    errors = []
+
+    def work(i):
+        try:
+            l, w = jobs[i]
+            for _ in range(3):
+                y = inputs[i].copy()
+                arr = y.reshape(-1, 3) if w == 3 else y
+                tf.ntt(arr)
+                if not np.array_equal(y, wants[i]):
+                    errors.append(f"job {i} mismatch")
+                leafs = inputs[i][: 5 * 64].reshape(64, 5).copy()
+                tf.MerkleTree.par_new(leafs)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

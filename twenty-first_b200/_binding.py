@@ -57,6 +57,7 @@ SIGNATURES = {
     "tf21_tip5_permute_dev": (i32, [vp, u64, vp]),
     "tf21_tip5_hash_10_dev": (i32, [vp, u64, vp, vp]),
     "tf21_tip5_hash_rows_dev": (i32, [vp, u64, u64, vp, vp]),
+    "tf21_tip5_hash_columns_dev": (i32, [vp, u64, u64, u64, vp, vp]),
     "tf21_merkle_build": (i32, [vp, u64, vp]),
     "tf21_merkle_root": (i32, [vp, u64, vp]),
     "tf21_merkle_build_dev": (i32, [vp, u64, vp, vp]),

@@ -450,7 +450,16 @@ int tf21_tip5_hash_rows_dev(const uint64_t *d_rows, uint64_t row_len, uint64_t n
                             tf21_stream_t stream) {
     DeviceTables *t;
     TF21_TRY(get_tables(&t));
-    return launch_hash_rows(d_rows, row_len, n_rows, d_out, (cudaStream_t)stream);
+    return launch_hash_rows(d_rows, row_len, n_rows, row_len, 1, d_out, (cudaStream_t)stream);
+}
+int tf21_tip5_hash_columns_dev(const uint64_t *d_cols, uint64_t n_rows, uint64_t n_cols, uint64_t col_stride_words,
+                               uint64_t *d_out, tf21_stream_t stream) {
+    if (n_rows == 0) return 0;
+    if (!d_out || (n_cols && !d_cols)) return TF21_E_BAD_ARG;
+    if (n_cols > 1 && col_stride_words < n_rows) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    return launch_hash_rows(d_cols, n_cols, n_rows, 1, col_stride_words, d_out, (cudaStream_t)stream);
 }
 
 int tf21_tip5_permute(uint64_t *states, uint64_t count) {

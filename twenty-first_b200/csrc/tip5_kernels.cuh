@@ -129,29 +129,32 @@ __global__ void __launch_bounds__(kMerkleTailThreads) merkle_tail_kernel(u64 *no
 }
 
 // Tip5::hash_varlen over rows (tip5/mod.rs:617-623, sponge.rs:41-56): one row per thread,
-// overwrite-mode absorb of 10-word chunks, padding 1,0,.. always present.
+// overwrite-mode absorb of 10-word chunks, padding 1,0,.. always present.  Element k of row i is
+// data[i * row_stride + k * elem_stride]: (row_len, 1) for a row-major matrix, (1, column stride)
+// for column-major data such as a batch of NTT codewords (coalesced across the threads of a warp).
 __global__ void __launch_bounds__(kTip5Threads)
-    tip5_hash_rows_kernel(const u64 *__restrict__ rows, u64 row_len, u64 n_rows, u64 *__restrict__ out) {
+    tip5_hash_rows_kernel(const u64 *__restrict__ data, u64 row_len, u64 n_rows, u64 row_stride, u64 elem_stride,
+                          u64 *__restrict__ out) {
     __shared__ uint8_t s_lut[256];
     tip5_load_lut(s_lut);
     __syncthreads();
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows) return;
-    const u64 *row = rows + i * row_len;
+    const u64 *row = data + i * row_stride;
     u64 s[TIP5_STATE];
 #pragma unroll
     for (int k = 0; k < TIP5_STATE; k++) s[k] = 0;
     u64 full = row_len / TIP5_RATE;
     for (u64 c = 0; c < full; c++) {
 #pragma unroll
-        for (int k = 0; k < TIP5_RATE; k++) s[k] = row[c * TIP5_RATE + k];
+        for (int k = 0; k < TIP5_RATE; k++) s[k] = row[(c * TIP5_RATE + k) * elem_stride];
         tip5_permutation(s, s_lut);
     }
     u32 rem = (u32)(row_len - full * TIP5_RATE);
 #pragma unroll
     for (int k = 0; k < TIP5_RATE; k++) {
         u64 v = 0;
-        if ((u32)k < rem) v = row[full * TIP5_RATE + k];
+        if ((u32)k < rem) v = row[(full * TIP5_RATE + k) * elem_stride];
         if ((u32)k == rem) v = TIP5_RAW_ONE;
         s[k] = v;
     }
@@ -196,10 +199,11 @@ inline int launch_hash10(const u64 *d_in, u64 count, u64 *d_out, cudaStream_t st
     return 0;
 }
 
-inline int launch_hash_rows(const u64 *d_rows, u64 row_len, u64 n_rows, u64 *d_out, cudaStream_t st) {
+inline int launch_hash_rows(const u64 *d_data, u64 row_len, u64 n_rows, u64 row_stride, u64 elem_stride,
+                            u64 *d_out, cudaStream_t st) {
     if (n_rows == 0) return 0;
-    TF21_LAUNCH(tip5_hash_rows_kernel, grid_for(n_rows, kTip5Threads), kTip5Threads, 0, st, d_rows, row_len,
-                n_rows, d_out);
+    TF21_LAUNCH(tip5_hash_rows_kernel, grid_for(n_rows, kTip5Threads), kTip5Threads, 0, st, d_data, row_len,
+                n_rows, row_stride, elem_stride, d_out);
     return 0;
 }
 

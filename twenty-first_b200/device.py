@@ -54,6 +54,11 @@ def tip5_hash_rows(rows: torch.Tensor, row_len: int, out: torch.Tensor) -> None:
     B.check(B.lib.tf21_tip5_hash_rows_dev(_p(rows), row_len, n_rows, _p(out), _stream()))
 
 
+def tip5_hash_columns(cols: torch.Tensor, n_rows: int, n_cols: int, out: torch.Tensor, col_stride: int = 0) -> None:
+    """digest i = hash_varlen(col_0[i], .., col_{n_cols-1}[i]) over column-major codewords"""
+    B.check(B.lib.tf21_tip5_hash_columns_dev(_p(cols), n_rows, n_cols, col_stride or n_rows, _p(out), _stream()))
+
+
 def merkle_build(leafs: torch.Tensor, nodes: torch.Tensor) -> None:
     B.check(B.lib.tf21_merkle_build_dev(_p(leafs), leafs.numel() // 5, _p(nodes), _stream()))
 
