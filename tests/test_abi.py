@@ -71,3 +71,14 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "oracle/" not in src, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/tf21.h must be consumable by a C compiler (the Rust/cgo/JNI side binds plain C)."""
+    import subprocess
+
+    src = tmp_path / "t.c"
+    src.write_text('#include "tf21.h"\nint main(void) { return tf21_strerror(TF21_E_CUDA) == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", f"-I{inc}", str(src)],
+                   check=True)

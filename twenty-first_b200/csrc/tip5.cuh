@@ -18,12 +18,6 @@
 #pragma once
 #include "field.cuh"
 
-#ifndef TIP5_MDS_ORDER
-#define TIP5_MDS_ORDER 0
-#endif
-#ifndef TIP5_MIN_BLOCKS
-#define TIP5_MIN_BLOCKS 1
-#endif
 #define TIP5_STATE 16
 #define TIP5_RATE 10
 #define TIP5_ROUNDS 5
@@ -34,6 +28,9 @@
 // zero-extended to u64, and the S-box table.
 __constant__ double c_tip5_rc_lo[TIP5_ROUNDS * TIP5_STATE];
 __constant__ double c_tip5_rc_hi[TIP5_ROUNDS * TIP5_STATE];
+// round-0 constants of fixed-length hashing: rc + sum_{j=10..15} M[(i-j)&15] * (ONE^7 mod p), per half
+__constant__ double c_tip5_rc0f_lo[TIP5_STATE];
+__constant__ double c_tip5_rc0f_hi[TIP5_STATE];
 __constant__ uint8_t c_tip5_lut[256];
 
 // MDS_MATRIX_FIRST_COLUMN, tip5/mod.rs:154-157
@@ -58,83 +55,66 @@ __device__ __forceinline__ u32 tip5_lut_word(u32 w, const uint8_t *s_lut) {
     return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
 }
 
+// One round.  NVAR = 16 in general; NVAR = 10 for the first round of fixed-length hashing
+// (hash_10 / hash_pair, tip5/mod.rs:511-526, 559-586) where lanes 10..15 hold the constant ONE: their
+// S-box outputs and MDS contributions are folded into the round-0 constants rc_lo / rc_hi passed in.
+template <int NVAR>
+__device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *s_lut, const double *rc_lo,
+                                           const double *rc_hi) {
+    // ---- S-box ----
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u32 lo = tip5_lut_word((u32)s[i], s_lut);
+        u32 hi = tip5_lut_word((u32)(s[i] >> 32), s_lut);
+        s[i] = gl_pack(lo, hi);
+    }
+#pragma unroll
+    for (int i = 4; i < NVAR; i++) {
+        u64 x = s[i];
+        u64 x2 = gl_mul(x, x);
+        u64 x4 = gl_mul(x2, x2);
+        u64 x6 = gl_mul(x2, x4);
+        s[i] = gl_mul(x, x6);
+    }
+    // ---- MDS + round constants (exact integer arithmetic on the FP64 pipe) ----
+    const double kBias = 4503599627370496.0;  // 2^52
+    double dl[NVAR], dh[NVAR];
+#pragma unroll
+    for (int j = 0; j < NVAR; j++) {
+        dl[j] = __hiloint2double(0x43300000, (int)(u32)s[j]) - kBias;
+        dh[j] = __hiloint2double(0x43300000, (int)(u32)(s[j] >> 32)) - kBias;
+    }
+#pragma unroll
+    for (int i = 0; i < TIP5_STATE; i++) {
+        double al = rc_lo[i];
+        double ah = rc_hi[i];
+#pragma unroll
+        for (int j = 0; j < NVAR; j++) {
+            const double m = (double)TIP5_MDS((i - j) & 15);
+            al = fma(m, dl[j], al);
+            ah = fma(m, dh[j], ah);
+        }
+        // al, ah < 2^52: adding 2^52 leaves the integer in the 52 mantissa bits
+        const u64 acc_lo = (u64)__double_as_longlong(al + kBias) & 0x000FFFFFFFFFFFFFull;
+        const u64 acc_hi = (u64)__double_as_longlong(ah + kBias) & 0x000FFFFFFFFFFFFFull;
+        // value = acc_lo + acc_hi * 2^32
+        u64 x0 = acc_lo + (acc_hi << 32);
+        u32 x1 = (u32)(acc_hi >> 32) + (x0 < acc_lo ? 1u : 0u);
+        u64 v = gl_reduce96(x0, x1);
+        s[i] = (i < 4) ? gl_canon(v) : v;
+    }
+}
+
 // s: 16 raw words as stored by the caller (the S-box LUT acts on the raw bytes as they are, like
 // split_and_lookup tip5/mod.rs:197-207; lanes 4..15 may be any representative mod p).
+// FIXED: lanes 10..15 are known to hold raw ONE (their contents are ignored).
 // On exit lanes 0..3 are canonical, lanes 4..15 weak; callers canonicalise what they store.
+template <bool FIXED = false>
 __device__ __forceinline__ void tip5_permutation(u64 (&s)[TIP5_STATE], const uint8_t *s_lut) {
+    if (FIXED) tip5_round<TIP5_RATE>(s, s_lut, c_tip5_rc0f_lo, c_tip5_rc0f_hi);
 #pragma unroll 1
-    for (int r = 0; r < TIP5_ROUNDS; r++) {
-        // ---- S-box ----
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            u32 lo = tip5_lut_word((u32)s[i], s_lut);
-            u32 hi = tip5_lut_word((u32)(s[i] >> 32), s_lut);
-            s[i] = gl_pack(lo, hi);
-        }
-#pragma unroll
-        for (int i = 4; i < TIP5_STATE; i++) {
-            u64 x = s[i];
-            u64 x2 = gl_mul(x, x);
-            u64 x4 = gl_mul(x2, x2);
-            u64 x6 = gl_mul(x2, x4);
-            s[i] = gl_mul(x, x6);
-        }
-        // ---- MDS + round constants (exact integer arithmetic on the FP64 pipe) ----
-        const double kBias = 4503599627370496.0;  // 2^52
-        double dl[TIP5_STATE], dh[TIP5_STATE];
-#pragma unroll
-        for (int j = 0; j < TIP5_STATE; j++) {
-            dl[j] = __hiloint2double(0x43300000, (int)(u32)s[j]) - kBias;
-            dh[j] = __hiloint2double(0x43300000, (int)(u32)(s[j] >> 32)) - kBias;
-        }
-#if TIP5_MDS_ORDER == 1
-        // j-outer: 32 independent accumulator chains (maximum ILP on the FP64 pipe)
-        double al[TIP5_STATE], ah[TIP5_STATE];
-#pragma unroll
-        for (int i = 0; i < TIP5_STATE; i++) {
-            al[i] = c_tip5_rc_lo[r * TIP5_STATE + i];
-            ah[i] = c_tip5_rc_hi[r * TIP5_STATE + i];
-        }
-#pragma unroll
-        for (int j = 0; j < TIP5_STATE; j++) {
-#pragma unroll
-            for (int i = 0; i < TIP5_STATE; i++) {
-                const double m = (double)TIP5_MDS((i - j) & 15);
-                al[i] = fma(m, dl[j], al[i]);
-                ah[i] = fma(m, dh[j], ah[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < TIP5_STATE; i++) {
-            const u64 acc_lo = (u64)__double_as_longlong(al[i] + kBias) & 0x000FFFFFFFFFFFFFull;
-            const u64 acc_hi = (u64)__double_as_longlong(ah[i] + kBias) & 0x000FFFFFFFFFFFFFull;
-            u64 x0 = acc_lo + (acc_hi << 32);
-            u32 x1 = (u32)(acc_hi >> 32) + (x0 < acc_lo ? 1u : 0u);
-            u64 v = gl_reduce96(x0, x1);
-            s[i] = (i < 4) ? gl_canon(v) : v;
-        }
-#else
-#pragma unroll
-        for (int i = 0; i < TIP5_STATE; i++) {
-            double al = c_tip5_rc_lo[r * TIP5_STATE + i];
-            double ah = c_tip5_rc_hi[r * TIP5_STATE + i];
-#pragma unroll
-            for (int j = 0; j < TIP5_STATE; j++) {
-                const double m = (double)TIP5_MDS((i - j) & 15);
-                al = fma(m, dl[j], al);
-                ah = fma(m, dh[j], ah);
-            }
-            // al, ah < 2^52: adding 2^52 leaves the integer in the 52 mantissa bits
-            const u64 acc_lo = (u64)__double_as_longlong(al + kBias) & 0x000FFFFFFFFFFFFFull;
-            const u64 acc_hi = (u64)__double_as_longlong(ah + kBias) & 0x000FFFFFFFFFFFFFull;
-            // value = acc_lo + acc_hi * 2^32
-            u64 x0 = acc_lo + (acc_hi << 32);
-            u32 x1 = (u32)(acc_hi >> 32) + (x0 < acc_lo ? 1u : 0u);
-            u64 v = gl_reduce96(x0, x1);
-            s[i] = (i < 4) ? gl_canon(v) : v;
-        }
-#endif
-    }
+    for (int r = FIXED ? 1 : 0; r < TIP5_ROUNDS; r++)
+        tip5_round<TIP5_STATE>(s, s_lut, c_tip5_rc_lo + r * TIP5_STATE, c_tip5_rc_hi + r * TIP5_STATE);
 }
 
 #endif

@@ -47,6 +47,25 @@ inline int upload_tip5_constants() {
         lo[i] = (double)(raw & 0xffffffffull);  // 32-bit halves: exact in a double
         hi[i] = (double)(raw >> 32);
     }
+    // fixed-length round 0: lanes 10..15 = ONE (raw 2^32 - 1); S-box there is ONE^7 on the raw word
+    double lo0[TIP5_STATE], hi0[TIP5_STATE];
+    {
+        const u64 c7 = hgl_pow(TIP5_RAW_ONE, 7);
+        const u64 c7_lo = c7 & 0xffffffffull, c7_hi = c7 >> 32;
+        static const u32 mds[16] = {61402, 1108, 28750, 33823, 7454, 43244, 53865, 12034,
+                                    56951, 27521, 41351, 40901, 12021, 59689, 26798, 17845};
+        for (int i = 0; i < TIP5_STATE; i++) {
+            u64 sl = 0, sh = 0;
+            for (int j = TIP5_RATE; j < TIP5_STATE; j++) {
+                sl += (u64)mds[(i - j) & 15] * c7_lo;
+                sh += (u64)mds[(i - j) & 15] * c7_hi;
+            }
+            lo0[i] = lo[i] + (double)sl;  // both < 2^51: exact
+            hi0[i] = hi[i] + (double)sh;
+        }
+    }
+    TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc0f_lo, lo0, sizeof(lo0)));
+    TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc0f_hi, hi0, sizeof(hi0)));
     uint8_t lut[256];
     // LOOKUP_TABLE, tip5/mod.rs:50-64 = ((x+1)^3 + 256) mod 257 (tip5/mod.rs:1022-1053)
     for (unsigned i = 0; i < 256; i++) lut[i] = (uint8_t)(((i + 1) * (i + 1) * (i + 1) + 256) % 257);
@@ -80,7 +99,7 @@ __global__ void __launch_bounds__(kTip5Threads) tip5_permute_kernel(u64 *__restr
 }
 
 // Tip5::hash_10 / hash_pair over a batch (tip5/mod.rs:559-586): state = in[0..10) | ONE x 6
-__global__ void __launch_bounds__(kTip5Threads, TIP5_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTip5Threads)
     tip5_hash10_kernel(const u64 *__restrict__ in, u64 count, u64 *__restrict__ out) {
     __shared__ uint8_t s_lut[256];
     tip5_load_lut(s_lut);
@@ -95,9 +114,7 @@ __global__ void __launch_bounds__(kTip5Threads, TIP5_MIN_BLOCKS)
         s[2 * k] = v.x;
         s[2 * k + 1] = v.y;
     }
-#pragma unroll
-    for (int k = TIP5_RATE; k < TIP5_STATE; k++) s[k] = TIP5_RAW_ONE;
-    tip5_permutation(s, s_lut);
+    tip5_permutation<true>(s, s_lut);  // capacity lanes = ONE, folded into the round-0 constants
     u64 *dst = out + 5 * i;
 #pragma unroll
     for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
@@ -116,9 +133,7 @@ __global__ void __launch_bounds__(kMerkleTailThreads) merkle_tail_kernel(u64 *no
             const u64 *src = nodes + 10ull * (cnt + i);
 #pragma unroll
             for (int k = 0; k < TIP5_RATE; k++) s[k] = src[k];
-#pragma unroll
-            for (int k = TIP5_RATE; k < TIP5_STATE; k++) s[k] = TIP5_RAW_ONE;
-            tip5_permutation(s, s_lut);
+            tip5_permutation<true>(s, s_lut);
             u64 *dst = nodes + 5ull * (cnt + i);
 #pragma unroll
             for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
