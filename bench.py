@@ -169,6 +169,7 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        os.environ["NCCL_DEBUG"] = os.environ.get("TF21_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout
         dist.init_process_group("nccl", device_id=cuda)
     dev.init(local_rank)
     peak_gbs, peak_src = load_peaks()
