@@ -93,7 +93,7 @@ def cpu_reference_leg(steps: int, warmup: int, sample_cols: int | None, merkle_l
     o.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cores = o.num_threads()
     n = 1 << LOG2N
-    cols = sample_cols or max(cores, 8)
+    cols = sample_cols or 128  # half of the 256-column batch: ~1 s of wall time per step on 16 threads
     x = oracle.splitmix64_words(0x210001, n * cols)
     orig = x.copy()
     for _ in range(max(1, min(warmup, 1))):
@@ -142,7 +142,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_leg(args.steps, args.warmup, args.cpu_cols, 20)
+        r = cpu_reference_leg(args.steps, args.warmup, args.cpu_cols, 22)
         line = {
             "impl": "reference", "metric": METRIC, "value": r["ntt_per_s"], "unit": "NTT/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
@@ -328,7 +328,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_reference_leg(2, 1, args.cpu_cols, 20)
+        r = cpu_reference_leg(2, 1, args.cpu_cols, 22)
         cpu = {"value": r["ntt_per_s"], "unit": "NTT/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                "merkle_leaves_per_s": r["merkle_leaves_per_s"]}
 

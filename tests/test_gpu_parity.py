@@ -447,3 +447,25 @@ def test_concurrent_callers_are_thread_safe(tf, oracle):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_ntt_four_pass_plan_2_27(tf, oracle):
+    """2^27 = 16 x 8 x 1024 x 1024 (two small passes + column pass + row pass): impulse response and
+    round trip (size-independent properties; the oracle would need minutes at this size)."""
+    n = 1 << 27
+    imp = np.zeros(n, dtype=np.uint64)
+    imp[3] = 0xFFFFFFFF  # raw one at position 3 -> omega^(3 i)
+    tf.ntt(imp)
+    omega = oracle.primitive_root_of_unity(n)
+    w3 = oracle.bfe_mod_pow(omega, 3)
+    for i in (0, 1, 2, 1023, 1024, 123456789 % n, n // 2, n - 1):
+        assert int(imp[i]) == oracle.bfe_mod_pow(w3, i), i
+    assert (imp < np.uint64(P)).all()
+    tf.intt(imp)
+    assert int(imp[3]) == 0xFFFFFFFF and np.count_nonzero(imp) == 1
+    x = rnd(0x2727, n)
+    y = x.copy()
+    tf.ntt(y)
+    assert not np.array_equal(x, y)
+    tf.intt(y)
+    assert np.array_equal(x, y)
