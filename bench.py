@@ -134,6 +134,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lde", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner)
+    # is diverted to stderr for the rest of the run
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -154,7 +159,7 @@ def main():
             "e2e": {"value": r["ntt_per_s"], "unit": "NTT/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "merkle": {"value": r["merkle_leaves_per_s"], "unit": "leaves/s"},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
         return
 
     import numpy as np
@@ -365,7 +370,7 @@ def main():
             "lde": lde, "cpu_baseline": cpu, "e2e": e2e, "clocks": clock_summary,
             "gpu_launches": int(l2 - l0), "gpu_launches_ntt": int(l1 - l0),
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
