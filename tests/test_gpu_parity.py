@@ -469,3 +469,36 @@ def test_ntt_four_pass_plan_2_27(tf, oracle):
     assert not np.array_equal(x, y)
     tf.intt(y)
     assert np.array_equal(x, y)
+
+
+def test_config1_full_batch_256_x_2_20(tf, oracle):
+    """BASELINE configs[1] at full size: 256 columns x 2^20 BFieldElement through the host-slice C ABI.
+    Eleven columns (random + adversarial) are compared word for word with the oracle, then the inverse
+    must restore all 2^28 input words."""
+    api = importlib.import_module("twenty-first_b200.api")
+    n, cols = 1 << 20, 256
+    x = rnd(0x210001, n * cols)
+    adv = adversarial(n)
+    x[5 * n: 6 * n] = adv[1]      # all p-1
+    x[6 * n: 7 * n] = adv[2]      # lanes 0xffffffff00000000
+    x[7 * n: 8 * n] = adv[4]      # impulse
+    orig = x.copy()
+    api.ntt_batch(x, n, 1, False)
+    assert (x < np.uint64(P)).all()
+    for c in (0, 1, 5, 6, 7, 17, 100, 128, 200, 254, 255):
+        want = orig[c * n: (c + 1) * n].copy()
+        assert oracle.ntt(want, 1) == 0
+        assert np.array_equal(x[c * n: (c + 1) * n], want), c
+    api.ntt_batch(x, n, 1, True)
+    assert np.array_equal(x, orig)
+
+
+def test_config2_merkle_2_24_full_node_array(tf, oracle):
+    """BASELINE configs[2] at full size: every one of the 2^25 node digests against the oracle."""
+    n = 1 << 24
+    leafs = rnd(0x210002, 5 * n)
+    rc, want = oracle.merkle_par_new(leafs)
+    assert rc == 0
+    tree = tf.MerkleTree.par_new(leafs.reshape(n, 5))
+    assert np.array_equal(tree.nodes.reshape(-1), want)
+    assert np.array_equal(tf.MerkleTree.par_frugal_root(leafs.reshape(n, 5)), want[5:10])
