@@ -48,6 +48,10 @@ extern "C" {
     pub fn tf21_coset_lde_dev(v: *const u64, n_in: u64, offset_in_raw: u64, n_out: u64, offset_out_raw: u64,
                               width: u32, out: *mut u64, s: tf21_stream_t) -> c_int;
 
+    pub fn tf21_poly_mul(a: *const u64, n_a: u64, b: *const u64, n_b: u64, width: u32, out: *mut u64) -> c_int;
+    pub fn tf21_poly_mul_dev(a: *const u64, n_a: u64, b: *const u64, n_b: u64, width: u32, out: *mut u64,
+                             s: tf21_stream_t) -> c_int;
+
     pub fn tf21_tip5_permute(states: *mut u64, count: u64) -> c_int;
     pub fn tf21_tip5_hash_10(input: *const u64, count: u64, out: *mut u64) -> c_int;
     pub fn tf21_tip5_hash_pairs(pairs: *const u64, count: u64, out: *mut u64) -> c_int;

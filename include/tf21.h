@@ -106,6 +106,16 @@ int tf21_coset_lde_dev(const uint64_t *d_values, uint64_t n_in, uint64_t offset_
                        uint64_t n_out, uint64_t offset_out_raw, uint32_t width, uint64_t *d_out,
                        tf21_stream_t stream);
 
+/* ---- next wave: Polynomial::fast_multiply (polynomial.rs:900-932) ------------- */
+/* out[0 .. n_a + n_b - 1) = a * b for two coefficient slices of the same width (1 = BFieldElement,
+ * 3 = XFieldElement): zero-extended NTTs of size next_power_of_two(n_a + n_b - 1), Hadamard product
+ * (Montgomery-correct), inverse NTT, truncation.  n_a == 0 or n_b == 0 is the zero polynomial:
+ * nothing is written.                                                                           */
+int tf21_poly_mul(const uint64_t *a, uint64_t n_a, const uint64_t *b, uint64_t n_b, uint32_t width,
+                  uint64_t *out);
+int tf21_poly_mul_dev(const uint64_t *d_a, uint64_t n_a, const uint64_t *d_b, uint64_t n_b, uint32_t width,
+                      uint64_t *d_out, tf21_stream_t stream);
+
 /* ---- Tip5 (tip5/mod.rs:529-533, 559-586, 617-623; sponge.rs:41-56) -------------------------- */
 int tf21_tip5_permute(uint64_t *states /*16 words each*/, uint64_t count);
 int tf21_tip5_hash_10(const uint64_t *in /*10 words each*/, uint64_t count, uint64_t *out /*5 each*/);

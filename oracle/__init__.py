@@ -76,6 +76,9 @@ class Oracle:
         L.oracle_coset_interpolate.argtypes = [_u64p, u64, u32, u64, _u64p]
         L.oracle_poly_evaluate.argtypes = [_u64p, u64, u64]
         L.oracle_poly_evaluate.restype = u64
+        L.oracle_poly_naive_multiply.argtypes = [_u64p, u64, _u64p, u64, u32, _u64p]
+        L.oracle_poly_naive_multiply.restype = None
+        L.oracle_poly_fast_multiply.argtypes = [_u64p, u64, _u64p, u64, u32, _u64p]
         L.oracle_tip5_permutation.argtypes = [_u64p]
         L.oracle_tip5_permutation.restype = None
         L.oracle_tip5_hash_10.argtypes = [_u64p, _u64p]
@@ -173,6 +176,19 @@ class Oracle:
         out = np.zeros(values.size, dtype=np.uint64)
         rc = self.lib.oracle_coset_interpolate(_ptr(values), values.size // width, width,
                                                offset_raw, _ptr(out))
+        return rc, out
+
+    def poly_naive_multiply(self, a: np.ndarray, b: np.ndarray, width: int) -> np.ndarray:
+        na, nb = a.size // width, b.size // width
+        out = np.zeros(max(0, na + nb - 1) * width if na and nb else 0, dtype=np.uint64)
+        if out.size:
+            self.lib.oracle_poly_naive_multiply(_ptr(a), na, _ptr(b), nb, width, _ptr(out))
+        return out
+
+    def poly_fast_multiply(self, a: np.ndarray, b: np.ndarray, width: int):
+        na, nb = a.size // width, b.size // width
+        out = np.zeros(max(0, na + nb - 1) * width if na and nb else 0, dtype=np.uint64)
+        rc = self.lib.oracle_poly_fast_multiply(_ptr(a), na, _ptr(b), nb, width, _ptr(out)) if out.size else 0
         return rc, out
 
     def poly_evaluate(self, coeffs: np.ndarray, x_raw: int) -> int:

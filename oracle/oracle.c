@@ -625,3 +625,56 @@ void oracle_set_num_threads(int n) {
     (void)n;
 #endif
 }
+
+/* ---- polynomial multiplication (next-wave checker) --------------------------------
+ * XFieldElement * XFieldElement, x_field_element.rs:512-535 ([c,b,a] = coefficients, mod x^3 - x + 1). */
+static void xfe_mul(const uint64_t l[3], const uint64_t r[3], uint64_t out[3]) {
+    uint64_t c = l[0], b = l[1], a = l[2], f = r[0], e = r[1], d = r[2];
+    uint64_t ae = bfe_mul(a, e), bd = bfe_mul(b, d), ad = bfe_mul(a, d);
+    out[0] = bfe_sub(bfe_sub(bfe_mul(c, f), ae), bd);
+    out[1] = bfe_add(bfe_add(bfe_sub(bfe_add(bfe_mul(b, f), bfe_mul(c, e)), ad), ae), bd);
+    out[2] = bfe_add(bfe_add(bfe_add(bfe_mul(a, f), bfe_mul(b, e)), bfe_mul(c, d)), ad);
+}
+
+/* schoolbook product (Polynomial::naive_multiply, polynomial.rs `naive_multiply`): out has na+nb-1 elements */
+void oracle_poly_naive_multiply(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint32_t w,
+                                uint64_t *out) {
+    if (na == 0 || nb == 0) return;
+    memset(out, 0, (na + nb - 1) * w * sizeof(uint64_t));
+    for (uint64_t i = 0; i < na; i++)
+        for (uint64_t j = 0; j < nb; j++) {
+            if (w == 1) {
+                out[i + j] = bfe_add(out[i + j], bfe_mul(a[i], b[j]));
+            } else {
+                uint64_t t[3];
+                xfe_mul(a + 3 * i, b + 3 * j, t);
+                for (int k = 0; k < 3; k++) out[3 * (i + j) + k] = bfe_add(out[3 * (i + j) + k], t[k]);
+            }
+        }
+}
+
+/* Polynomial::fast_multiply, polynomial.rs:900-932: resize to the next power of two, ntt both,
+ * Hadamard product, intt, truncate. */
+int oracle_poly_fast_multiply(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint32_t w,
+                              uint64_t *out) {
+    if (na == 0 || nb == 0) return 0;
+    uint64_t len = na + nb - 1, order = 1;
+    while (order < len) order <<= 1;
+    uint64_t *l = calloc(order * w, sizeof(uint64_t)), *r = calloc(order * w, sizeof(uint64_t));
+    if (!l || !r) { free(l); free(r); return -6; }
+    memcpy(l, a, na * w * sizeof(uint64_t));
+    memcpy(r, b, nb * w * sizeof(uint64_t));
+    int rc = oracle_ntt(l, order, w);
+    if (!rc) rc = oracle_ntt(r, order, w);
+    if (!rc) {
+        for (uint64_t i = 0; i < order; i++) {
+            if (w == 1) l[i] = bfe_mul(l[i], r[i]);
+            else { uint64_t t[3]; xfe_mul(l + 3 * i, r + 3 * i, t); memcpy(l + 3 * i, t, sizeof(t)); }
+        }
+        rc = oracle_intt(l, order, w);
+    }
+    if (!rc) memcpy(out, l, len * w * sizeof(uint64_t));
+    free(l);
+    free(r);
+    return rc;
+}

@@ -30,6 +30,10 @@ int oracle_coset_evaluate(const uint64_t *coeffs, uint64_t n_coeffs, uint32_t w,
                           uint64_t order, uint64_t *out);
 int oracle_coset_interpolate(const uint64_t *values, uint64_t n, uint32_t w, uint64_t offset_raw,
                              uint64_t *coeffs_out);
+void oracle_poly_naive_multiply(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint32_t w,
+                                uint64_t *out);
+int oracle_poly_fast_multiply(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint32_t w,
+                              uint64_t *out);
 uint64_t oracle_poly_evaluate(const uint64_t *coeffs, uint64_t n_coeffs, uint64_t x_raw);
 
 void oracle_tip5_permutation(uint64_t state[16]);

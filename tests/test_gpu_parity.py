@@ -502,3 +502,35 @@ def test_config2_merkle_2_24_full_node_array(tf, oracle):
     tree = tf.MerkleTree.par_new(leafs.reshape(n, 5))
     assert np.array_equal(tree.nodes.reshape(-1), want)
     assert np.array_equal(tf.MerkleTree.par_frugal_root(leafs.reshape(n, 5)), want[5:10])
+
+
+@pytest.mark.parametrize("na,nb,width", [(1, 1, 1), (1, 1, 3), (2, 2, 1), (5, 3, 3), (33, 31, 1), (64, 65, 3),
+                                         (1000, 25, 1), (1 << 12, 1 << 12, 1), (3000, 5000, 3),
+                                         (1 << 17, (1 << 17) + 1, 1), (1 << 19, 1 << 19, 3)])
+def test_poly_fast_multiply_matches_oracle(tf, oracle, na, nb, width):
+    """next wave (SURVEY.md 8f-2): Polynomial::fast_multiply on the device, every coefficient vs the oracle"""
+    a, b = rnd(0x900 + na, na * width), rnd(0x901 + nb, nb * width)
+    if na * nb <= 1 << 16:
+        want = oracle.poly_naive_multiply(a, b, width)
+    else:
+        rc, want = oracle.poly_fast_multiply(a, b, width)
+        assert rc == 0
+    pa = tf.Polynomial(a.reshape(na, 3) if width == 3 else a)
+    pb = tf.Polynomial(b.reshape(nb, 3) if width == 3 else b)
+    got = pa.fast_multiply(pb).coefficients
+    assert np.array_equal(got.reshape(-1), want)
+    assert (got < np.uint64(P)).all()
+
+
+def test_poly_multiply_evaluation_property(tf, oracle):
+    """(a * b)(x) == a(x) * b(x) at random points (size-independent check at 2^21-coefficient operands)"""
+    na = nb = 1 << 21
+    a, b = rnd(0xA1, na), rnd(0xB1, nb)
+    prod = tf.Polynomial(a).fast_multiply(tf.Polynomial(b)).coefficients
+    assert prod.shape[0] == na + nb - 1
+    for seed in (1, 2, 3):
+        x = int(rnd(0xE0 + seed, 1)[0])
+        assert oracle.poly_evaluate(prod, x) == oracle.bfe_mul(oracle.poly_evaluate(a, x), oracle.poly_evaluate(b, x))
+    # zero polynomial
+    z = tf.Polynomial(np.zeros(0, dtype=np.uint64)).fast_multiply(tf.Polynomial(a[:4].copy()))
+    assert z.coefficients.size == 0

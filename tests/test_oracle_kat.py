@@ -299,3 +299,27 @@ def test_coset_xfe_lanes_independent(oracle):
     rc, vals_n = oracle.coset_evaluate(coeffs, 3, g, n)
     rc, back = oracle.coset_interpolate(vals_n, 3, g)
     assert np.array_equal(back, coeffs)
+
+
+def test_poly_multiply_naive_equals_fast_and_doc_example(oracle):
+    """polynomial.rs doc example (2 + 3x)^2 = 4 + 12x + 9x^2 (:806-808) and the reference's property
+    `fast_multiply == naive_multiply` for both field types."""
+    import oracle as o
+
+    a = oracle.to_raw([2, 3])
+    sq = oracle.poly_naive_multiply(a, a, 1)
+    assert [int(v) for v in oracle.to_values(sq)] == [4, 12, 9]
+    rc, sqf = oracle.poly_fast_multiply(a, a, 1)
+    assert rc == 0 and np.array_equal(sq, sqf)
+    for w in (1, 3):
+        for na, nb in ((1, 1), (1, 7), (5, 3), (33, 31), (64, 65), (200, 57)):
+            x, y = o.splitmix64_words(na * 31 + nb, na * w), o.splitmix64_words(nb * 17 + na + 5, nb * w)
+            rc, f = oracle.poly_fast_multiply(x, y, w)
+            assert rc == 0
+            assert np.array_equal(f, oracle.poly_naive_multiply(x, y, w)), (w, na, nb)
+    # XFE product restates x_field_element.rs:512-535: x * x^2 = x^3 = x - 1 (mod x^3 - x + 1)
+    one, zero = oracle.to_raw([1])[0], np.uint64(0)
+    xx = np.array([zero, one, zero], dtype=np.uint64)
+    x2 = np.array([zero, zero, one], dtype=np.uint64)
+    got = oracle.poly_naive_multiply(xx, x2, 3)
+    assert [int(v) for v in oracle.to_values(got)] == [(1 << 64) - (1 << 32) + 1 - 1, 1, 0]

@@ -49,6 +49,8 @@ SIGNATURES = {
     "tf21_coset_evaluate_dev": (i32, [vp, u64, u32, u64, u64, vp, vp]),
     "tf21_coset_interpolate_dev": (i32, [vp, u64, u32, u64, vp, vp]),
     "tf21_coset_lde_dev": (i32, [vp, u64, u64, u64, u64, u32, vp, vp]),
+    "tf21_poly_mul": (i32, [vp, u64, vp, u64, u32, vp]),
+    "tf21_poly_mul_dev": (i32, [vp, u64, vp, u64, u32, vp, vp]),
     "tf21_tip5_permute": (i32, [vp, u64]),
     "tf21_tip5_hash_10": (i32, [vp, u64, vp]),
     "tf21_tip5_hash_pairs": (i32, [vp, u64, vp]),

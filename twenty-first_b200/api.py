@@ -96,6 +96,17 @@ class Polynomial:
                                           offset_raw, order, _ptr(out)))
         return out
 
+    def fast_multiply(self, other: "Polynomial") -> "Polynomial":
+        """polynomial.rs:900-932 (same-width operands); trailing zero coefficients are kept"""
+        if self.width != other.width:
+            raise TypeError("mixed BFieldElement / XFieldElement products are not offloaded")
+        na, nb = self.coefficients.shape[0], other.coefficients.shape[0]
+        n = na + nb - 1 if na and nb else 0
+        out = np.zeros((n,) if self.width == 1 else (n, 3), dtype=np.uint64)
+        B.check(B.lib.tf21_poly_mul(_ptr(self.coefficients), na, _ptr(other.coefficients), nb, self.width,
+                                    _ptr(out)))
+        return Polynomial(out)
+
     @staticmethod
     def fast_coset_interpolate(offset_raw: int, values: np.ndarray) -> "Polynomial":
         """polynomial.rs:1907-1918"""

@@ -27,9 +27,17 @@
 
 namespace tf21 {
 
-constexpr u32 kFastCols = 8;        // word-columns (= warps) per CTA
-constexpr u32 kFastS = 1058;        // u64 per column slice in shared memory (>= 32 * 33)
+#ifndef TF21_FAST_COLS
+#define TF21_FAST_COLS 8
+#endif
+constexpr u32 kFastCols = TF21_FAST_COLS;  // word-columns (= warps) per CTA: 4, 8 or 16
+// u64 per column slice in shared memory (>= 32 * 33), chosen so that the staging pattern
+// (kFastCols lanes per row segment) is bank-conflict free: 2 S mod 32 = 64 / kFastCols
+constexpr u32 kFastS = kFastCols == 4 ? 1060 : kFastCols == 8 ? 1058 : 1057;
 constexpr u32 kFastThreads = kFastCols * 32;
+constexpr u32 kFastMinBlocks = 16 / kFastCols;  // 512 threads of 128 registers per SM
+constexpr u32 kStageRowsPerIt = 32 / kFastCols;  // rows covered by one warp instruction of the staging loops
+constexpr u32 kStageRowsPerWarp = 1024 / kFastCols;
 constexpr size_t kFastSmem = (size_t)kFastCols * kFastS * sizeof(u64);
 
 __host__ __device__ constexpr u32 brev5(u32 k) {
@@ -131,7 +139,7 @@ struct FastColArgs {
 };
 
 template <bool INV>
-__global__ void __launch_bounds__(kFastThreads, 2) ntt1024_col_kernel(const FastColArgs a) {
+__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kernel(const FastColArgs a) {
     extern __shared__ u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,7 +148,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_col_kernel(const Fast
     const u32 o = rest % a.n_outer, b = rest / a.n_outer;
     const u64 q0 = (u64)ct * kFastCols;
     const u64 inner_elems = a.inner_words / a.w;
-    const u32 c = lane & 7, rsub = lane >> 3;
+    const u32 c = lane % kFastCols, rsub = lane / kFastCols;
 
     // ---- stage in: 8 lanes per 64-byte row segment, 4 rows per warp instruction ----
     const u64 block_off = (u64)o * 1024 * a.inner_words + q0;
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_col_kernel(const Fast
         u64 *tl = tile + c * kFastS;
 #pragma unroll 8
         for (u32 it = 0; it < 32; it++) {
-            const u32 r = warp * 128 + it * 4 + rsub;
+            const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
             const u64 j = ((u64)o * 1024 + r) * inner_elems + jcol;
             u64 x = 0;
             if (j < a.n_in_elems) {
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_col_kernel(const Fast
         const u64 *tl = tile + c * kFastS;
 #pragma unroll 8
         for (u32 it = 0; it < 32; it++) {
-            const u32 r = warp * 128 + it * 4 + rsub;
+            const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
             dst[(u64)r * a.inner_words] = tl[r];
         }
     }
@@ -212,7 +220,7 @@ struct FastRowArgs {
 // consecutive word-columns tc = o' * w + c of the output; a warp loads its row directly (stride w),
 // the transposed store goes through shared memory; canonical on store.
 template <bool INV, u32 W>
-__global__ void __launch_bounds__(kFastThreads, 2) ntt1024_row_kernel(const FastRowArgs a) {
+__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kernel(const FastRowArgs a) {
     extern __shared__ u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_row_kernel(const Fast
 
     // stage out: word (i_k = r, tc) -> dst[r * rows * w + tc]
     {
-        const u32 c8 = lane & 7, rsub = lane >> 3;
+        const u32 c8 = lane % kFastCols, rsub = lane / kFastCols;
         const u32 tc = tc0 + c8;
         u64 *dst = a.dst + (u64)b * a.array_words + tc;
         const u64 *tl = tile + c8 * kFastS;
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) ntt1024_row_kernel(const Fast
         const u64 op = tc / W;  // element index = op + rows * r
 #pragma unroll 8
         for (u32 it = 0; it < 32; it++) {
-            const u32 r = warp * 128 + it * 4 + rsub;
+            const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
             u64 x = tl[r];
             if (a.post_scalar) x = gl_mul(x, a.post_scalar);
             if (a.post.lo) x = gl_mul(x, scale_factor_l(a.post, op + (u64)rows * r));
@@ -400,7 +408,7 @@ struct FastSingleArgs {
 
 // n = 1024, w = 1: one warp per array of the batch, no global staging at all.
 template <bool INV>
-__global__ void __launch_bounds__(kFastThreads, 2) ntt1024_single_kernel(const FastSingleArgs a) {
+__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_single_kernel(const FastSingleArgs a) {
     extern __shared__ u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -205,6 +205,29 @@ __global__ void ntt_row_pass_kernel(const RowPassArgs a) {
     }
 }
 
+// ---- Hadamard product for Polynomial::fast_multiply (polynomial.rs:923-927) ------------------------
+// The operands are raw Montgomery words, so the reference's `l * r` is (l_raw * r_raw) * R^-1 mod p per
+// BFieldElement product; every term of the XFieldElement product (x_field_element.rs:512-535) is a
+// product of exactly two words, so the whole result is the plain mod-p product times `rinv` = 2^-64.
+// Output words are lazy (any u64): the inverse transform that follows accepts any representative.
+__global__ void hadamard_kernel(u64 *__restrict__ a, const u64 *__restrict__ b, u64 n_elems, u32 w, u64 rinv) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_elems) return;
+    if (w == 1) {
+        a[i] = gl_mul(gl_mul(a[i], b[i]), rinv);
+        return;
+    }
+    const u64 c = a[3 * i], bb = a[3 * i + 1], aa = a[3 * i + 2];
+    const u64 f = b[3 * i], e = b[3 * i + 1], d = b[3 * i + 2];
+    const u64 ae = gl_mulc(aa, e), bd = gl_mulc(bb, d), ad = gl_mulc(aa, d);
+    const u64 r0 = gl_sub(gl_sub(gl_mulc(c, f), ae), bd);
+    const u64 r1 = gl_add(gl_add(gl_sub(gl_add(gl_mulc(bb, f), gl_mulc(c, e)), ad), ae), bd);
+    const u64 r2 = gl_add(gl_add(gl_add(gl_mulc(aa, f), gl_mulc(bb, e)), gl_mulc(c, d)), ad);
+    a[3 * i] = gl_mul(r0, rinv);
+    a[3 * i + 1] = gl_mul(r1, rinv);
+    a[3 * i + 2] = gl_mul(r2, rinv);
+}
+
 // ---- host planning ------------------------------------------------------------------------------
 
 inline size_t col_pass_smem(u32 log_np) {

@@ -435,6 +435,57 @@ int tf21_coset_lde(const uint64_t *values, uint64_t n_in, uint64_t offset_in_raw
     return 0;
 }
 
+// ---- polynomial multiplication (next wave) -----------------------------------------
+int tf21_poly_mul_dev(const uint64_t *d_a, uint64_t n_a, const uint64_t *d_b, uint64_t n_b, uint32_t width,
+                      uint64_t *d_out, tf21_stream_t stream) {
+    if (width != 1 && width != 3) return TF21_E_BAD_ARG;
+    if (n_a == 0 || n_b == 0) return 0;  // zero polynomial: nothing to write (polynomial.rs:909-911)
+    if (!d_a || !d_b || !d_out) return TF21_E_BAD_ARG;
+    const u64 len = n_a + n_b - 1;
+    u64 order = 1;
+    while (order < len) order <<= 1;  // (degree + 1).next_power_of_two(), polynomial.rs:912
+    TF21_TRY(check_ntt_len(order, width));
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch l(st), r(st);
+    TF21_TRY(l.alloc(order * width));
+    TF21_TRY(r.alloc(order * width));
+    // resize(order, ZERO) + ntt, fused: the transforms read only the n_a / n_b coefficients that exist
+    TF21_TRY(ntt_run_locked(*t, d_a, n_a, l.p, order, width, 1, 0, NO_SCALE, NO_SCALE, 0, st));
+    TF21_TRY(ntt_run_locked(*t, d_b, n_b, r.p, order, width, 1, 0, NO_SCALE, NO_SCALE, 0, st));
+    const u64 rinv = hgl_inv(GL_EPS);  // 2^-64 mod p
+    TF21_LAUNCH(hadamard_kernel, grid_for(order, 256), 256, 0, st, l.p, r.p, order, width, rinv);
+    const u64 post_scalar = hgl_inv(order % GL_P);
+    if (order == len) {
+        TF21_TRY(ntt_run_locked(*t, l.p, order, d_out, order, width, 1, 1, NO_SCALE, NO_SCALE,
+                                order > 1 ? post_scalar : 0, st));
+        if (order == 1) {  // identity transform: still canonicalise the lazy product
+            TF21_TRY(tf21_selftest_field_dev(3, d_out, d_out, d_out, width, stream));
+        }
+    } else {
+        TF21_TRY(ntt_run_locked(*t, l.p, order, r.p, order, width, 1, 1, NO_SCALE, NO_SCALE, post_scalar, st));
+        TF21_CUDA(cudaMemcpyAsync(d_out, r.p, len * width * sizeof(u64), cudaMemcpyDeviceToDevice, st));  // truncate
+    }
+    return 0;
+}
+
+int tf21_poly_mul(const uint64_t *a, uint64_t n_a, const uint64_t *b, uint64_t n_b, uint32_t width, uint64_t *out) {
+    if (width != 1 && width != 3) return TF21_E_BAD_ARG;
+    if (n_a == 0 || n_b == 0) return 0;
+    if (!a || !b || !out) return TF21_E_BAD_ARG;
+    const u64 len = n_a + n_b - 1;
+    DevBuf da, db, dout;
+    TF21_TRY(da.alloc(n_a * width));
+    TF21_TRY(db.alloc(n_b * width));
+    TF21_TRY(dout.alloc(len * width));
+    TF21_CUDA(cudaMemcpy(da.p, a, n_a * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_CUDA(cudaMemcpy(db.p, b, n_b * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_poly_mul_dev(da.p, n_a, db.p, n_b, width, dout.p, nullptr));
+    TF21_CUDA(cudaMemcpy(out, dout.p, len * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // ---- Tip5 ------------------------------------------------------------------------------------------
 int tf21_tip5_permute_dev(uint64_t *d_states, uint64_t count, tf21_stream_t stream) {
     DeviceTables *t;
