@@ -18,6 +18,9 @@
 #pragma once
 #include "field.cuh"
 
+#ifndef TIP5_CVT
+#define TIP5_CVT 3  /* measured -2.4 % on the Merkle build (tools/ab.sh); bit 0: I2F instead of the 2^52 bias on input; bit 1: F2I on output */
+#endif
 #define TIP5_STATE 16
 #define TIP5_RATE 10
 #define TIP5_ROUNDS 5
@@ -81,8 +84,13 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
     double dl[NVAR], dh[NVAR];
 #pragma unroll
     for (int j = 0; j < NVAR; j++) {
+#if TIP5_CVT & 1
+        dl[j] = __uint2double_rn((u32)s[j]);
+        dh[j] = __uint2double_rn((u32)(s[j] >> 32));
+#else
         dl[j] = __hiloint2double(0x43300000, (int)(u32)s[j]) - kBias;
         dh[j] = __hiloint2double(0x43300000, (int)(u32)(s[j] >> 32)) - kBias;
+#endif
     }
 #pragma unroll
     for (int i = 0; i < TIP5_STATE; i++) {
@@ -95,8 +103,13 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
             ah = fma(m, dh[j], ah);
         }
         // al, ah < 2^52: adding 2^52 leaves the integer in the 52 mantissa bits
+#if TIP5_CVT & 2
+        const u64 acc_lo = __double2ull_rn(al);
+        const u64 acc_hi = __double2ull_rn(ah);
+#else
         const u64 acc_lo = (u64)__double_as_longlong(al + kBias) & 0x000FFFFFFFFFFFFFull;
         const u64 acc_hi = (u64)__double_as_longlong(ah + kBias) & 0x000FFFFFFFFFFFFFull;
+#endif
         // value = acc_lo + acc_hi * 2^32
         u64 x0 = acc_lo + (acc_hi << 32);
         u32 x1 = (u32)(acc_hi >> 32) + (x0 < acc_lo ? 1u : 0u);
