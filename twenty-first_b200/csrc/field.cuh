@@ -21,7 +21,7 @@ typedef uint32_t u32;
 #define GL_EPS 0xFFFFFFFFull /* 2^64 mod p */
 
 #ifndef TF21_SHL_WIDE
-#define TF21_SHL_WIDE 1  /* measured +1.6 % on the 2^20 batch (tools/ab.sh) */
+#define TF21_SHL_WIDE 1  /* 0: shifts on the ALU (-1.8 %), 1: two IMAD.WIDE with a 64-bit addend (best), 2: OR instead of the addend (-1.7 %); tools/ab.sh on the 2^20 batch */
 #endif
 #ifndef TF21_SUB_WIDE
 #define TF21_SUB_WIDE 0  /* measured -3 %: the FMA pipe is as loaded as the ALU pipe */
@@ -241,11 +241,18 @@ __device__ __forceinline__ u64 gl_canonw(u64 x) {
 __device__ __forceinline__ u64 gl_shlc(u64 x, const int S) {
     const int q = S >> 5, t = S & 31;
     const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
-#if TF21_SHL_WIDE
+#if TF21_SHL_WIDE >= 1
     const u32 mt = c_gl_pow2[t];
     const u64 p0 = (u64)x0 * mt;
-    const u64 p1 = (u64)x1 * mt + (p0 >> 32);
-    const u32 z0 = (u32)p0, z1 = (u32)p1, z2 = (u32)(p1 >> 32);
+    const u64 p1 = (u64)x1 * mt;
+#if TF21_SHL_WIDE == 2
+    // hi(p0) < 2^t and the low t bits of lo(p1) are zero: OR instead of a 64-bit addend (which costs two
+    // register moves to build the (hi(p0), 0) pair)
+    const u32 z0 = (u32)p0, z1 = (u32)p1 | (u32)(p0 >> 32), z2 = (u32)(p1 >> 32);
+#else
+    const u64 p1a = p1 + (p0 >> 32);
+    const u32 z0 = (u32)p0, z1 = (u32)p1a, z2 = (u32)(p1a >> 32);
+#endif
 #else
     const u32 z0 = x0 << t;
     const u32 z1 = __funnelshift_l(x0, x1, t);
