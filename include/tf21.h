@@ -71,7 +71,7 @@ int tf21_stream_sync(tf21_stream_t stream);
  * the Goldilocks primitives): op 0 add, 1 sub, 2 mul (all mod p, canonical result), 3 canonicalise,
  * 4 weak add then canonicalise, 5 reduce a 96-bit value a + (b & 0xffffffff) * 2^64,
  * 6 lazy add (a any, b <= p) then canonicalise, 7 canonicalise (IMAD.WIDE form), 8 lazy sub (a any,
- * b < p) then canonicalise, 100+S: a * 2^S mod p for the shift twiddles S (S % 3 == 0 or S in
+ * b < p) then canonicalise, 9 the butterfly form of the lazy sub (b <= p), 100+S: a * 2^S mod p for the shift twiddles S (S % 3 == 0 or S in
  * {1,31,65,95}), canonical result for any a.                                                    */
 int tf21_selftest_field_dev(int op, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out,
                             uint64_t n, tf21_stream_t stream);

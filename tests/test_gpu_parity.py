@@ -90,6 +90,7 @@ def test_device_field_primitives(tf):
     assert run(6, dwa, dwbp) == [(x + int(y)) % P for x, y in zip(wai, wbp)]
     assert run(7, dwa, dwb) == [x % P for x in wai]
     assert run(8, dwa, dwbc) == [(x - int(y)) % P for x, y in zip(wai, wbc)]
+    assert run(9, dwa, dwbp) == [(x - int(y)) % P for x, y in zip(wai, wbp)]
     for s in list(range(3, 96, 3)) + [1, 31, 65, 95]:
         assert run(100 + s, dwa, dwb) == [(x << s) % P for x in wai], f"shift {s}"
 

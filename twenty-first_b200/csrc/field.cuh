@@ -23,6 +23,9 @@ typedef uint32_t u32;
 #ifndef TF21_SHL_WIDE
 #define TF21_SHL_WIDE 1  /* 0: shifts on the ALU (-1.8 %), 1: two IMAD.WIDE with a 64-bit addend (best), 2: OR instead of the addend (-1.7 %); tools/ab.sh on the 2^20 batch */
 #endif
+#ifndef TF21_PRED_FIX
+#define TF21_PRED_FIX 1
+#endif
 #ifndef TF21_SUB_WIDE
 #define TF21_SUB_WIDE 0  /* measured -3 %: the FMA pipe is as loaded as the ALU pipe */
 #endif
@@ -199,10 +202,69 @@ __device__ __forceinline__ u64 gl_mul_pow2(u64 x, const int S) {
 // s + c * EPS (mod 2^64), c in {0,1}.  Compiles to a single IMAD.WIDE.U32.
 __device__ __forceinline__ u64 gl_fix(u64 s, u32 c) { return s + (u64)c * GL_EPS; }
 
+// ---- wrap corrections as predicated instructions ---------------------------------------------------
+// Written with an explicit branch around the 64-bit correction: ptxas folds the materialised carry back
+// into the carry predicate of the IADD3.X and if-converts the two-instruction body, so a lazy add is
+// IADD3, IADD3.X, @P IADD3, @P IADD3.X -- no SEL, no IMAD.WIDE.  Subtraction is a + ~b + 1 so that only
+// add-with-carry instructions appear (borrow and carry flags are never mixed, see gl_canon).
+__device__ __forceinline__ u64 gl_addp(u64 a, u64 t) {  // a any, t <= p -> any
+    u64 s;
+    asm("{\n\t.reg .u32 c; .reg .pred p; .reg .u64 v;\n\t"
+        "add.cc.u64 v,%1,%2;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.eq.u32 p,c,0;\n\t"
+        "@p bra GLA%=;\n\t"
+        "add.u64 v,v,0xffffffff;\n\t"
+        "GLA%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(s)
+        : "l"(a), "l"(t));
+    return s;
+}
+__device__ __forceinline__ u64 gl_subp(u64 a, u64 t) {  // a any, t <= p -> any; both < p -> result < p
+    u64 s;
+    asm("{\n\t.reg .u32 lo,hi,c,d,n0,n1; .reg .pred p; .reg .u64 v;\n\t"
+        "not.b32 n0,%3;\n\t"
+        "not.b32 n1,%4;\n\t"
+        "add.cc.u32 d,0xffffffff,1;\n\t"
+        "addc.cc.u32 lo,%1,n0;\n\t"
+        "addc.cc.u32 hi,%2,n1;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.ne.u32 p,c,0;\n\t"
+        "mov.b64 v,{lo,hi};\n\t"
+        "@p bra GLS%=;\n\t"
+        "sub.u64 v,v,0xffffffff;\n\t"
+        "GLS%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(s)
+        : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)t), "r"((u32)(t >> 32)));
+    return s;
+}
+__device__ __forceinline__ u64 gl_canonp(u64 x) {  // any -> [0, p)
+    u64 s;
+    asm("{\n\t.reg .u32 lo,hi; .reg .pred p1,p2; .reg .u64 v;\n\t"
+        "mov.b64 {lo,hi},%1;\n\t"
+        "mov.b64 v,%1;\n\t"
+        "setp.eq.u32 p1,hi,0xffffffff;\n\t"
+        "setp.ne.and.u32 p2,lo,0,p1;\n\t"
+        "@!p2 bra GLC%=;\n\t"
+        "add.u64 v,v,0xffffffff;\n\t"
+        "GLC%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(s)
+        : "l"(x));
+    return s;
+}
+
 // lazy sub for the butterflies: a any u64, t <= p -> any u64.  With TF21_SUB_WIDE the wrap correction
 // d - bw * EPS = (lo, hi - bw) + bw is one signed IMAD.WIDE (m * m + .., m = -bw) instead of two ALU ops.
 __device__ __forceinline__ u64 gl_subl(u64 a, u64 t) {
-#if TF21_SUB_WIDE
+#if TF21_PRED_FIX
+    return gl_subp(a, t);
+#elif TF21_SUB_WIDE
     u32 lo, hi, m;
     asm("sub.cc.u32 %0,%3,%5;\n\tsubc.cc.u32 %1,%4,%6;\n\tsubc.u32 %2,0,0;"
         : "=r"(lo), "=r"(hi), "=r"(m)
@@ -216,6 +278,9 @@ __device__ __forceinline__ u64 gl_subl(u64 a, u64 t) {
 
 // lazy add: a any u64, t <= p  ->  any u64 (value a + t mod p).  3 ALU + 1 IMAD.WIDE.
 __device__ __forceinline__ u64 gl_addl(u64 a, u64 t) {
+#if TF21_PRED_FIX
+    return gl_addp(a, t);
+#endif
     u32 lo, hi, c;
     asm("add.cc.u32 %0,%3,%5;\n\taddc.cc.u32 %1,%4,%6;\n\taddc.u32 %2,0,0;"
         : "=r"(lo), "=r"(hi), "=r"(c)
@@ -225,6 +290,9 @@ __device__ __forceinline__ u64 gl_addl(u64 a, u64 t) {
 
 // any u64 -> [0, p):  x >= p  <=>  hi == 0xffffffff && lo != 0.  2 ISETP + SEL + 1 IMAD.WIDE.
 __device__ __forceinline__ u64 gl_canonw(u64 x) {
+#if TF21_PRED_FIX
+    return gl_canonp(x);
+#endif
     u32 f;
     asm("{\n\t.reg .pred p1, p2;\n\t"
         "setp.eq.u32 p1, %2, 0xffffffff;\n\t"
@@ -264,19 +332,36 @@ __device__ __forceinline__ u64 gl_shlc(u64 x, const int S) {
         asm("mad.lo.cc.u32 %0,%5,0xffffffff,%3;\n\tmadc.hi.cc.u32 %1,%5,0xffffffff,%4;\n\taddc.u32 %2,0,0;"
             : "=r"(lo), "=r"(hi), "=r"(c)
             : "r"(z0), "r"(z1), "r"(z2));
+#if TF21_PRED_FIX
+        u64 r;
+        asm("{\n\t.reg .pred p1,p2,p3; .reg .u64 v;\n\t"
+            "mov.b64 v,{%1,%2};\n\t"
+            "setp.eq.u32 p1,%2,0xffffffff;\n\t"
+            "setp.ne.and.u32 p2,%1,0,p1;\n\t"
+            "setp.ne.or.u32 p3,%3,0,p2;\n\t"
+            "@!p3 bra GLQ%=;\n\t"
+            "add.u64 v,v,0xffffffff;\n\t"
+            "GLQ%=:\n\t"
+            "mov.b64 %0,v;\n\t"
+            "}"
+            : "=l"(r)
+            : "r"(lo), "r"(hi), "r"(c));
+        return r;
+#else
         const u32 f = c | ((hi == 0xffffffffu && lo != 0) ? 1u : 0u);
         return gl_fix(gl_pack(lo, hi), f);
+#endif
     } else if (q == 1) {
         // z * 2^32 = (z0 + z1) 2^32 - (z1 + z2):  T1 = (s : -carry) < p,  T2 = z1 + z2 < 2^33
         const u32 s = z0 + z1;
         const u32 c = (s < z0) ? 1u : 0u;
         const u64 T1 = gl_pack(0u - c, s);
         const u64 T2 = (u64)z1 + (u64)z2;
-        return gl_sub(T1, T2);
+        return gl_subl(T1, T2);
     } else {
         // z * 2^64 = z0 * EPS - (z2:z1):  z0 * EPS <= (2^32-1)^2 < p, (z2:z1) < 2^63
         const u64 a = (u64)z0 * GL_EPS;
-        return gl_sub(a, gl_pack(z1, z2));
+        return gl_subl(a, gl_pack(z1, z2));
     }
 }
 
