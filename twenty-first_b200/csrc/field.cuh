@@ -20,11 +20,14 @@ typedef uint32_t u32;
 #define GL_P 0xFFFFFFFF00000001ull
 #define GL_EPS 0xFFFFFFFFull /* 2^64 mod p */
 
+#ifndef TF21_PRED_FIX
+#define TF21_PRED_FIX 1  /* wrap corrections as predicated instructions (+4 % on the 2^20 batch) */
+#endif
+#ifndef TF21_PRED_MUL
+#define TF21_PRED_MUL 1
+#endif
 #ifndef TF21_SHL_WIDE
 #define TF21_SHL_WIDE 1  /* 0: shifts on the ALU (-1.8 %), 1: two IMAD.WIDE with a 64-bit addend (best), 2: OR instead of the addend (-1.7 %); tools/ab.sh on the 2^20 batch */
-#endif
-#ifndef TF21_PRED_FIX
-#define TF21_PRED_FIX 1
 #endif
 #ifndef TF21_SUB_WIDE
 #define TF21_SUB_WIDE 0  /* measured -3 %: the FMA pipe is as loaded as the ALU pipe */
@@ -136,11 +139,54 @@ __device__ __forceinline__ u64 gl_reduce128(u32 r0, u32 r1, u32 r2, u32 r3) {
     return gl_pack(lo, hi);
 }
 
+// Same reduction with the two wrap corrections as predicated instructions (see gl_addp below):
+// (r1:r0) + ~r3 + 1 in the carry domain, "no carry" = borrow -> -EPS; then + r2 * EPS, carry -> +EPS.
+__device__ __forceinline__ u64 gl_reduce128p(u32 r0, u32 r1, u32 r2, u32 r3) {
+    u64 out;
+    asm("{\n\t.reg .u32 lo,hi,c,d,n3; .reg .pred p; .reg .u64 v;\n\t"
+        "not.b32 n3,%4;\n\t"
+        "add.cc.u32 d,0xffffffff,1;\n\t"
+        "addc.cc.u32 lo,%1,n3;\n\t"
+        "addc.cc.u32 hi,%2,0xffffffff;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.ne.u32 p,c,0;\n\t"
+        "mov.b64 v,{lo,hi};\n\t"
+        "@p bra GLR1%=;\n\t"
+        "sub.u64 v,v,0xffffffff;\n\t"
+        "GLR1%=:\n\t"
+        "mov.b64 {lo,hi},v;\n\t"
+        "mad.lo.cc.u32 lo,%3,0xffffffff,lo;\n\t"
+        "madc.hi.cc.u32 hi,%3,0xffffffff,hi;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.eq.u32 p,c,0;\n\t"
+        "mov.b64 v,{lo,hi};\n\t"
+        "@p bra GLR2%=;\n\t"
+        "add.u64 v,v,0xffffffff;\n\t"
+        "GLR2%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(out)
+        : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
+    return out;
+}
+
+// mask-style reduction regardless of TF21_PRED_MUL: two registers less pressure than the predicated
+// form inside the 1024-point column kernel (which otherwise spills)
+__device__ __forceinline__ u64 gl_mul_mask(u64 a, u64 b) {
+    u32 r0, r1, r2, r3;
+    gl_mul128(a, b, r0, r1, r2, r3);
+    return gl_reduce128(r0, r1, r2, r3);
+}
+
 // a * b mod p; a, b any u64 -> any u64
 __device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {
     u32 r0, r1, r2, r3;
     gl_mul128(a, b, r0, r1, r2, r3);
+#if TF21_PRED_MUL
+    return gl_reduce128p(r0, r1, r2, r3);
+#else
     return gl_reduce128(r0, r1, r2, r3);
+#endif
 }
 
 // canonical product
@@ -148,6 +194,24 @@ __device__ __forceinline__ u64 gl_mulc(u64 a, u64 b) { return gl_canon(gl_mul(a,
 
 // 96-bit value x0 + x1 2^64 (x1 < 2^32) -> any u64
 __device__ __forceinline__ u64 gl_reduce96(u64 x0, u32 x1) {
+#if TF21_PRED_FIX
+    u64 out;
+    asm("{\n\t.reg .u32 lo,hi,c; .reg .pred p; .reg .u64 v;\n\t"
+        "mov.b64 {lo,hi},%1;\n\t"
+        "mad.lo.cc.u32 lo,%2,0xffffffff,lo;\n\t"
+        "madc.hi.cc.u32 hi,%2,0xffffffff,hi;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.eq.u32 p,c,0;\n\t"
+        "mov.b64 v,{lo,hi};\n\t"
+        "@p bra GLN%=;\n\t"
+        "add.u64 v,v,0xffffffff;\n\t"
+        "GLN%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(out)
+        : "l"(x0), "r"(x1));
+    return out;
+#endif
     u32 lo, hi, m;
     asm("{\n\t"
         "mad.lo.cc.u32  %0, %5, 0xffffffff, %3;\n\t"
@@ -306,8 +370,10 @@ __device__ __forceinline__ u64 gl_canonw(u64 x) {
 // x * 2^S mod p with a CANONICAL result; x any u64; compile-time 0 < S < 96 with S % 32 != 0
 // (every shift twiddle of a 32- or 64-point transform: S is a multiple of 3).
 // z = x << (S % 32) as three 32-bit limbs, then fold by 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32.
-__device__ __forceinline__ u64 gl_shlc(u64 x, const int S) {
-    const int q = S >> 5, t = S & 31;
+template <int S>
+__device__ __forceinline__ u64 gl_shlc(u64 x) {
+    static_assert(S > 0 && S < 96 && (S & 31) != 0, "shift twiddle out of range");
+    constexpr int q = S >> 5, t = S & 31;
     const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
 #if TF21_SHL_WIDE >= 1
     const u32 mt = c_gl_pow2[t];
@@ -326,7 +392,7 @@ __device__ __forceinline__ u64 gl_shlc(u64 x, const int S) {
     const u32 z1 = __funnelshift_l(x0, x1, t);
     const u32 z2 = x1 >> (32 - t);  // < 2^31
 #endif
-    if (q == 0) {
+    if constexpr (q == 0) {
         // (z1:z0) + z2 * EPS, z2 * EPS < 2^63: at most one wrap; carry and "r >= p" are exclusive
         u32 lo, hi, c;
         asm("mad.lo.cc.u32 %0,%5,0xffffffff,%3;\n\tmadc.hi.cc.u32 %1,%5,0xffffffff,%4;\n\taddc.u32 %2,0,0;"
@@ -351,7 +417,7 @@ __device__ __forceinline__ u64 gl_shlc(u64 x, const int S) {
         const u32 f = c | ((hi == 0xffffffffu && lo != 0) ? 1u : 0u);
         return gl_fix(gl_pack(lo, hi), f);
 #endif
-    } else if (q == 1) {
+    } else if constexpr (q == 1) {
         // z * 2^32 = (z0 + z1) 2^32 - (z1 + z2):  T1 = (s : -carry) < p,  T2 = z1 + z2 < 2^33
         const u32 s = z0 + z1;
         const u32 c = (s < z0) ? 1u : 0u;

@@ -53,34 +53,44 @@ __host__ __device__ constexpr u32 brev_bits(u32 k, int bits) {
 // v[brev_A(k)] = sum_a x[a] w^(a k) (any u64), w = omega_{2^A}^(+-1) = 2^(+-39 * 2^(6-A)) because
 // omega_64 = 2^39 (PRIMITIVE_ROOTS, b_field_element.rs:43-78).  (butterfly of ntt.rs:203-210; the
 // twiddles are shifts; exponents >= 96 use 2^96 = -1 and swap the roles of sum and difference)
+// One butterfly per template instance (LS = stage, IDX = butterfly index inside the stage): every
+// register index and every shift amount is a compile-time constant by construction, so the value
+// array can never fall back to local memory (a `#pragma unroll` loop nest around inline asm with
+// labels was left partially rolled by the compiler for some sizes).
+template <bool INV, int A, int LS, int IDX>
+__device__ __forceinline__ void dft_pow2_step(u64 (&v)[1 << A]) {
+    constexpr int N = 1 << A;
+    if constexpr (LS > A) {
+        return;
+    } else if constexpr (IDX >= N / 2) {
+        dft_pow2_step<INV, A, LS + 1, 0>(v);
+    } else {
+        constexpr int EU = (39 << (6 - A)) % 192;
+        constexpr int m = 1 << LS, half = m >> 1;
+        constexpr int k = (IDX / half) * m, j = IDX % half;
+        constexpr int iu = brev_bits(k + j, A), ib = brev_bits(k + j + half, A);
+        constexpr int E0 = (EU * j * (N / m)) % 192;
+        constexpr int E = INV ? (192 - E0) % 192 : E0;
+        constexpr bool neg = E >= 96;
+        constexpr int S = neg ? E - 96 : E;
+        u64 t;
+        if constexpr (S == 0) t = gl_canonw(v[ib]);
+        else t = gl_shlc<S>(v[ib]);
+        const u64 u = v[iu];
+        if constexpr (!neg) {
+            v[iu] = gl_addl(u, t);
+            v[ib] = gl_subl(u, t);
+        } else {
+            v[iu] = gl_subl(u, t);
+            v[ib] = gl_addl(u, t);
+        }
+        dft_pow2_step<INV, A, LS, IDX + 1>(v);
+    }
+}
+
 template <bool INV, int A>
 __device__ __forceinline__ void dft_pow2(u64 (&v)[1 << A]) {
-    constexpr int N = 1 << A;
-    constexpr int EU = (39 << (6 - A)) % 192;
-#pragma unroll
-    for (int ls = 1; ls <= A; ls++) {
-        const int m = 1 << ls, half = m >> 1;
-#pragma unroll
-        for (int k = 0; k < N; k += m) {
-#pragma unroll
-            for (int j = 0; j < half; j++) {
-                const int iu = brev_bits(k + j, A), ib = brev_bits(k + j + half, A);
-                int E = (EU * j * (N / m)) % 192;
-                if (INV) E = (192 - E) % 192;
-                const bool neg = E >= 96;
-                const int S = neg ? E - 96 : E;
-                const u64 t = (S == 0) ? gl_canonw(v[ib]) : gl_shlc(v[ib], S);
-                const u64 u = v[iu];
-                if (!neg) {
-                    v[iu] = gl_addl(u, t);
-                    v[ib] = gl_subl(u, t);
-                } else {
-                    v[iu] = gl_subl(u, t);
-                    v[ib] = gl_addl(u, t);
-                }
-            }
-        }
-    }
+    dft_pow2_step<INV, A, 1, 0>(v);
 }
 
 template <bool INV>
@@ -98,7 +108,7 @@ __device__ __forceinline__ u64 scale_factor_l(const ScaleTab &t, u64 idx) {
 // out: slice[i] = X[i] * (tw1 ? tw1[32 (i >> 5)] : 1), i = lane + 32 k2   (any u64)
 // slice: this warp's kFastS-word shared-memory slice; tw0 = t1 + lane with t1[k1*32+b] = w1024^(k1 b);
 // tw1: per-lane pointer into the inter-pass twiddle row (or nullptr).
-template <bool INV>
+template <bool INV, bool MASKMUL = false>
 __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64 *tw0, const u64 *tw1, u32 lane) {
 #pragma unroll 1
     for (int it = 0; it < 2; it++) {
@@ -109,7 +119,8 @@ __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64
         __syncwarp();
         if (tw) {
 #pragma unroll
-            for (int k = 0; k < 32; k++) out[k * ss] = gl_mul(v[brev5(k)], __ldg(tw + 32 * k));
+            for (int k = 0; k < 32; k++)
+                out[k * ss] = MASKMUL ? gl_mul_mask(v[brev5(k)], __ldg(tw + 32 * k)) : gl_mul(v[brev5(k)], __ldg(tw + 32 * k));
         } else {
 #pragma unroll
             for (int k = 0; k < 32; k++) out[k * ss] = v[brev5(k)];
@@ -177,7 +188,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
     for (int aa = 0; aa < 32; aa++) v[aa] = slice[32 * aa + lane];
     const u64 jrest = (q0 + warp) / a.w;
     // inter-pass twiddle omega_B^(i * j_rest), i = lane + 32 k2: straight from the full table when there is one
-    dft1024_warp<INV>(v, slice, a.t1 + lane, a.tw_full ? a.tw_full + jrest * 1024 + lane : nullptr, lane);
+    dft1024_warp<INV, true>(v, slice, a.t1 + lane, a.tw_full ? a.tw_full + jrest * 1024 + lane : nullptr, lane);
     if (!a.tw_full) {
         const u64 bmask = (1ull << a.log_b) - 1;
 #pragma unroll 4
@@ -327,6 +338,56 @@ __global__ void __launch_bounds__(128) ntt_small_col_kernel(const SmallColArgs a
     }
 }
 
+// shift-twiddled inputs of one output group d of the pruned pass: z[r] = x[r] * w^(r d)
+template <int A, int LNZ, int D, int R>
+__device__ __forceinline__ void pruned_twiddle(const u64 (&x)[1 << LNZ], u64 (&z)[1 << LNZ]) {
+    if constexpr (R < (1 << LNZ)) {
+        constexpr int EU = (39 << (6 - A)) % 192;
+        constexpr int E = (EU * R * D) % 192;
+        constexpr bool neg = E >= 96;
+        constexpr int S = neg ? E - 96 : E;
+        u64 t;
+        if constexpr (S == 0) t = x[R];
+        else t = gl_shlc<S>(x[R]);
+        if constexpr (neg) t = gl_subl(0ull, gl_canonw(t));
+        z[R] = t;
+        pruned_twiddle<A, LNZ, D, R + 1>(x, z);
+    }
+}
+
+template <int A, int LNZ, int D, int C>
+__device__ __forceinline__ void pruned_store(u64 (&z)[1 << LNZ], u64 *dst, const u64 *tcol, u64 inner_elems,
+                                             u64 inner_words, u64 &tc, u64 gM) {
+    if constexpr (C < (1 << LNZ)) {
+        constexpr int M = (1 << A) >> LNZ;
+        constexpr int i = M * C + D;
+        u64 v = z[brev_bits(C, LNZ)];
+        if (tcol) {
+            v = gl_mul(v, __ldg(tcol + (u64)i * inner_elems));
+        } else {
+            if constexpr (i != 0) v = gl_mul(v, tc);
+            if constexpr (C + 1 < (1 << LNZ)) tc = gl_mul(tc, gM);
+        }
+        dst[(u64)i * inner_words] = v;
+        pruned_store<A, LNZ, D, C + 1>(z, dst, tcol, inner_elems, inner_words, tc, gM);
+    }
+}
+
+template <int A, int LNZ, int D>
+__device__ __forceinline__ void pruned_steps(const u64 (&x)[1 << LNZ], u64 *dst, const u64 *tcol, u64 inner_elems,
+                                             u64 inner_words, u64 g, u64 gM, u64 gd) {
+    constexpr int M = (1 << A) >> LNZ;
+    if constexpr (D < M) {
+        u64 z[1 << LNZ];
+        pruned_twiddle<A, LNZ, D, 0>(x, z);
+        dft_pow2<false, LNZ>(z);
+        u64 tc = gd;
+        pruned_store<A, LNZ, D, 0>(z, dst, tcol, inner_elems, inner_words, tc, gM);
+        if (!tcol) gd = gl_mul(gd, g);
+        pruned_steps<A, LNZ, D + 1>(x, dst, tcol, inner_elems, inner_words, g, gM, gd);
+    }
+}
+
 // Pruned column pass for zero-extended inputs (the `resize(order, ZERO)` of fast_coset_evaluate,
 // polynomial.rs:1396-1397): only the first NZ = 2^LNZ rows of a 2^A-point column can be non-zero, so
 // with M = 2^A / NZ and k = M c + d:  X[M c + d] = sum_{a < NZ} (x_a w^(a d)) w_NZ^(a c)  -- for every d one
@@ -365,34 +426,7 @@ __global__ void __launch_bounds__(128) ntt_small_col_pruned_kernel(const SmallCo
 #pragma unroll
         for (int k = 0; k < A - LNZ; k++) gM = gl_mul(gM, gM);
     }
-#pragma unroll
-    for (int d = 0; d < M; d++) {
-        u64 z[NZ];
-#pragma unroll
-        for (int r = 0; r < NZ; r++) {
-            const int E = (EU * r * d) % 192;
-            const bool neg = E >= 96;
-            const int S = neg ? E - 96 : E;
-            u64 t = (S == 0) ? x[r] : gl_shlc(x[r], S);
-            if (neg) t = gl_sub(0ull, gl_canonw(t));
-            z[r] = t;
-        }
-        dft_pow2<false, LNZ>(z);
-        u64 tc = gd;
-#pragma unroll
-        for (int c = 0; c < NZ; c++) {
-            const int i = M * c + d;
-            u64 v = z[brev_bits(c, LNZ)];
-            if (tcol) {
-                v = gl_mul(v, __ldg(tcol + (u64)i * inner_elems));
-            } else {
-                if (i != 0) v = gl_mul(v, tc);
-                if (c + 1 < NZ) tc = gl_mul(tc, gM);
-            }
-            dst[(u64)i * a.inner_words] = v;
-        }
-        if (!tcol && d + 1 < M) gd = gl_mul(gd, g);
-    }
+    pruned_steps<A, LNZ, 0>(x, dst, tcol, inner_elems, a.inner_words, g, gM, gd);
 }
 
 struct FastSingleArgs {

@@ -222,7 +222,7 @@ __global__ void selftest_field_kernel(int op, const u64 *a, const u64 *b, u64 *o
         case 7: r = gl_canonw(x); break;
         case 8: r = gl_canon(gl_sub(x, y)); break;   // x any, y < p
         case 9: r = gl_canon(gl_subl(x, y)); break;  // x any, y <= p (butterfly form)
-#define TF21_SHL_CASE(S) case 100 + (S): r = gl_shlc(x, (S)); break;
+#define TF21_SHL_CASE(S) case 100 + (S): r = gl_shlc<S>(x); break;
             TF21_SHL_CASE(3) TF21_SHL_CASE(6) TF21_SHL_CASE(9) TF21_SHL_CASE(12) TF21_SHL_CASE(15)
             TF21_SHL_CASE(18) TF21_SHL_CASE(21) TF21_SHL_CASE(24) TF21_SHL_CASE(27) TF21_SHL_CASE(30)
             TF21_SHL_CASE(33) TF21_SHL_CASE(36) TF21_SHL_CASE(39) TF21_SHL_CASE(42) TF21_SHL_CASE(45)
