@@ -21,14 +21,18 @@
 #ifndef TIP5_CVT
 #define TIP5_CVT 3  /* measured -2.4 % on the Merkle build (tools/ab.sh); bit 0: I2F instead of the 2^52 bias on input; bit 1: F2I on output */
 #endif
+#ifndef TIP5_MDS_CRT
+#define TIP5_MDS_CRT 1  /* MDS as cyclic-8 + negacyclic-8 products (CRT over x^16 - 1): 320 instead of 512 FP64 ops per round */
+#endif
 #define TIP5_STATE 16
 #define TIP5_RATE 10
 #define TIP5_ROUNDS 5
 #define TIP5_DIGEST 5
 #define TIP5_RAW_ONE 0xFFFFFFFFull /* BFieldElement::ONE as a raw word = 2^64 mod p */
 
-// Filled by upload_tip5_constants (tip5_kernels.cuh): raw round constants split in 32-bit halves,
-// zero-extended to u64, and the S-box table.
+// Filled by upload_tip5_constants (tip5_kernels.cuh): raw round constants split in 32-bit halves (with
+// TIP5_MDS_CRT stored as the seeds of the two half-size products: [i] = (rc_i + rc_(i+8))/2,
+// [8 + i] = (rc_i - rc_(i+8))/2, i < 8), and the S-box table.
 __constant__ double c_tip5_rc_lo[TIP5_ROUNDS * TIP5_STATE];
 __constant__ double c_tip5_rc_hi[TIP5_ROUNDS * TIP5_STATE];
 // round-0 constants of fixed-length hashing: rc + sum_{j=10..15} M[(i-j)&15] * (ONE^7 mod p), per half
@@ -92,6 +96,58 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
         dh[j] = __hiloint2double(0x43300000, (int)(u32)(s[j] >> 32)) - kBias;
 #endif
     }
+#if TIP5_MDS_CRT
+    // t(x) = M(x) s(x) mod (x^16 - 1) by the CRT split x^16 - 1 = (x^8 - 1)(x^8 + 1):
+    //   a = s_lo + s_hi, b = s_lo - s_hi;  P = (M_lo + M_hi)/2 * a mod (x^8 - 1)  (cyclic),
+    //   Q = (M_lo - M_hi)/2 * b mod (x^8 + 1) (negacyclic);  t_lo = P + Q, t_hi = P - Q.
+    // 2 x 64 multiply-adds + 32 additions per half instead of 256 multiply-adds.  Exact: every partial sum is a
+    // multiple of 1/2 with |2 P| <= t_i + t_(i+8) < 2^53 and |2 Q| < 2^53 (sum of the column = 524757 < 2^19.01,
+    // inputs < 2^32, seeds = halves of sums/differences of the round constants).  rc_lo / rc_hi hold the seeds:
+    // [0..8) for P = (rc_i + rc_(i+8))/2, [8..16) for Q = (rc_i - rc_(i+8))/2.
+    double al[8], ah[8], bl[8], bh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (j + 8 < NVAR) {
+            al[j] = dl[j] + dl[j + 8];
+            bl[j] = dl[j] - dl[j + 8];
+            ah[j] = dh[j] + dh[j + 8];
+            bh[j] = dh[j] - dh[j + 8];
+        } else {  // lane j + 8 is constant: folded into the seeds
+            al[j] = bl[j] = dl[j];
+            ah[j] = bh[j] = dh[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        double pl = rc_lo[i], ph = rc_hi[i], ql = rc_lo[8 + i], qh = rc_hi[8 + i];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = (i - j) & 7;
+            const double mp = 0.5 * ((double)TIP5_MDS(k) + (double)TIP5_MDS(k + 8));
+            const double mn = (j <= i ? 0.5 : -0.5) * ((double)TIP5_MDS(k) - (double)TIP5_MDS(k + 8));
+            pl = fma(mp, al[j], pl);
+            ph = fma(mp, ah[j], ph);
+            ql = fma(mn, bl[j], ql);
+            qh = fma(mn, bh[j], qh);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const double tl = half ? pl - ql : pl + ql;
+            const double th = half ? ph - qh : ph + qh;
+#if TIP5_CVT & 2
+            const u64 acc_lo = __double2ull_rn(tl);
+            const u64 acc_hi = __double2ull_rn(th);
+#else
+            const u64 acc_lo = (u64)__double_as_longlong(tl + kBias) & 0x000FFFFFFFFFFFFFull;
+            const u64 acc_hi = (u64)__double_as_longlong(th + kBias) & 0x000FFFFFFFFFFFFFull;
+#endif
+            u64 x0 = acc_lo + (acc_hi << 32);
+            u32 x1 = (u32)(acc_hi >> 32) + (x0 < acc_lo ? 1u : 0u);
+            const u64 v = gl_reduce96(x0, x1);
+            s[i + 8 * half] = (i + 8 * half < 4) ? gl_canon(v) : v;
+        }
+    }
+#else
 #pragma unroll
     for (int i = 0; i < TIP5_STATE; i++) {
         double al = rc_lo[i];
@@ -116,6 +172,7 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
         u64 v = gl_reduce96(x0, x1);
         s[i] = (i < 4) ? gl_canon(v) : v;
     }
+#endif
 }
 
 // s: 16 raw words as stored by the caller (the S-box LUT acts on the raw bytes as they are, like

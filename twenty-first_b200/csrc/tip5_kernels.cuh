@@ -64,6 +64,22 @@ inline int upload_tip5_constants() {
             hi0[i] = hi[i] + (double)sh;
         }
     }
+#if TIP5_MDS_CRT
+    // seeds of the cyclic / negacyclic half-size products (tip5.cuh): halves of sums and differences, exact
+    auto to_seeds = [](double *v) {
+        for (int i = 0; i < 8; i++) {
+            const double a = v[i], b = v[i + 8];
+            v[i] = 0.5 * (a + b);
+            v[i + 8] = 0.5 * (a - b);
+        }
+    };
+    to_seeds(lo0);
+    to_seeds(hi0);
+    for (int r = 0; r < TIP5_ROUNDS; r++) {
+        to_seeds(lo + r * TIP5_STATE);
+        to_seeds(hi + r * TIP5_STATE);
+    }
+#endif
     TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc0f_lo, lo0, sizeof(lo0)));
     TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc0f_hi, hi0, sizeof(hi0)));
     uint8_t lut[256];
