@@ -42,6 +42,8 @@ enum {
     TF21_E_ALLOC = -6,           /* MerkleTreeError::TreeTooHigh, merkle_tree.rs:403-410 / cudaMalloc */
     TF21_E_CUDA = -7,            /* any CUDA runtime failure; see tf21_last_cuda_error()             */
     TF21_E_BAD_ARG = -8,         /* width not in {1,3}, NULL pointer with non-zero size, ...         */
+    TF21_E_LEAF_INDEX_INVALID = -9, /* MerkleTreeError::LeafIndexInvalid, merkle_tree.rs:487-489       */
+    TF21_E_CAPACITY = -10,       /* output buffer smaller than the result; *count holds the need     */
 };
 
 typedef void *tf21_stream_t; /* cudaStream_t */
@@ -153,6 +155,36 @@ int tf21_merkle_root_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d_
 int tf21_merkle_scatter_subtree_dev(const uint64_t *d_local_nodes, uint64_t n_local_leafs,
                                     uint64_t shard, uint64_t n_shards, uint64_t *d_global_nodes,
                                     tf21_stream_t stream);
+
+/* ---- next wave: authentication structures (merkle_tree.rs:449-542, 614-622) ---- */
+/* MerkleTree::authentication_structure_node_indices: node indices needed to prove the given leaf
+ * indices, descending, de-duplicated.  Pure host logic (no device).  *count is always set to the number
+ * of indices; TF21_E_CAPACITY if it exceeds `capacity` (call with out = NULL, capacity = 0 to size).   */
+int tf21_merkle_auth_structure_node_indices(uint64_t n_leafs, const uint64_t *leaf_indices,
+                                            uint64_t n_indices, uint64_t *out, uint64_t capacity,
+                                            uint64_t *count);
+/* MerkleTree::authentication_structure of a device-resident node array (as tf21_merkle_build_dev leaves
+ * it): d_out[k] = nodes[index_k], 5 words each.  leaf_indices is a host array.                         */
+int tf21_merkle_authentication_structure_dev(const uint64_t *d_nodes, uint64_t n_leafs,
+                                             const uint64_t *leaf_indices, uint64_t n_indices,
+                                             uint64_t *d_out, uint64_t capacity, uint64_t *count,
+                                             tf21_stream_t stream);
+/* MerkleTree::{sequential,par}_authentication_structure_from_leafs: host leaves in, host digests out. */
+int tf21_merkle_authentication_structure_from_leafs(const uint64_t *leafs, uint64_t n_leafs,
+                                                    const uint64_t *leaf_indices, uint64_t n_indices,
+                                                    uint64_t *out, uint64_t capacity, uint64_t *count);
+
+/* ---- next wave: MMR bulk operations (mmr/mmr_accumulator.rs:96-115, 379-391) ------- */
+/* MmrAccumulator::peaks_from_leafs for any leaf count: *n_peaks = popcount(n_leafs) digests are written
+ * (at most 64).  n_leafs == 0 writes nothing.                                                          */
+int tf21_mmr_peaks_from_leafs(const uint64_t *leafs, uint64_t n_leafs, uint64_t *peaks_out,
+                              uint64_t *n_peaks);
+int tf21_mmr_peaks_from_leafs_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d_peaks_out,
+                                  uint64_t *n_peaks, tf21_stream_t stream);
+/* bag_peaks(peaks, leaf_count): hash_10 of the encoded leaf count folded over the peaks from the last. */
+int tf21_mmr_bag_peaks(const uint64_t *peaks, uint64_t n_peaks, uint64_t leaf_count, uint64_t out[5]);
+int tf21_mmr_bag_peaks_dev(const uint64_t *d_peaks, uint64_t n_peaks, uint64_t leaf_count,
+                           uint64_t *d_out, tf21_stream_t stream);
 
 #ifdef __cplusplus
 }

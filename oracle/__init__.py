@@ -28,6 +28,7 @@ E_LEN_TOO_LARGE = -2
 E_TOO_FEW_LEAFS = -3
 E_INCORRECT_NUMBER_OF_LEAFS = -4
 E_ORDER_LE_DEGREE = -5
+E_LEAF_INDEX_INVALID = -9
 
 
 def build(native: bool = False, force: bool = False) -> str:
@@ -99,6 +100,12 @@ class Oracle:
         L.oracle_merkle_par_new.argtypes = [_u64p, u64, _u64p, i32, u64]
         L.oracle_merkle_sequential_frugal_root.argtypes = [_u64p, u64, _u64p]
         L.oracle_merkle_par_frugal_root.argtypes = [_u64p, u64, _u64p, i32, u64]
+        L.oracle_mmr_peaks_from_leafs.argtypes = [_u64p, u64, _u64p]
+        L.oracle_mmr_peaks_from_leafs.restype = u64
+        L.oracle_mmr_bag_peaks.argtypes = [_u64p, u64, u64, _u64p]
+        L.oracle_mmr_bag_peaks.restype = None
+        L.oracle_auth_structure_node_indices.argtypes = [u64, _u64p, u64, _u64p]
+        L.oracle_auth_structure_node_indices.restype = ctypes.c_int64
         for name in ("new", "value", "inverse_or_zero", "primitive_root_of_unity"):
             f = getattr(L, f"oracle_bfe_{name}")
             f.argtypes = [u64]
@@ -258,6 +265,31 @@ class Oracle:
         root = np.zeros(5, dtype=np.uint64)
         rc = self.lib.oracle_merkle_par_frugal_root(_ptr(leafs if n else root), n, _ptr(root), threads, cutoff)
         return rc, root
+
+    def mmr_peaks_from_leafs(self, leafs: np.ndarray) -> np.ndarray:
+        """MmrAccumulator::peaks_from_leafs (mmr_accumulator.rs:96-115), any leaf count"""
+        n = leafs.size // 5
+        peaks = np.zeros(64 * 5, dtype=np.uint64)
+        k = self.lib.oracle_mmr_peaks_from_leafs(_ptr(leafs if n else peaks), n, _ptr(peaks))
+        return peaks[: 5 * k].reshape(-1, 5).copy()
+
+    def mmr_bag_peaks(self, peaks: np.ndarray, leaf_count: int) -> np.ndarray:
+        out = np.zeros(5, dtype=np.uint64)
+        peaks = np.ascontiguousarray(peaks, dtype=np.uint64).reshape(-1)
+        buf = peaks if peaks.size else np.zeros(5, dtype=np.uint64)
+        self.lib.oracle_mmr_bag_peaks(_ptr(buf), peaks.size // 5, leaf_count, _ptr(out))
+        return out
+
+    def auth_structure_node_indices(self, num_leafs: int, leaf_indices):
+        """(rc, indices): MerkleTree::authentication_structure_node_indices (merkle_tree.rs:449-504)"""
+        idx = np.ascontiguousarray(np.array(leaf_indices, dtype=np.uint64))
+        height = max(1, int(num_leafs).bit_length())
+        out = np.zeros(idx.size * height + 1, dtype=np.uint64)
+        buf = idx if idx.size else np.zeros(1, dtype=np.uint64)
+        rc = self.lib.oracle_auth_structure_node_indices(num_leafs, _ptr(buf), idx.size, _ptr(out))
+        if rc < 0:
+            return rc, None
+        return 0, out[:rc].copy()
 
     def num_threads(self) -> int:
         return self.lib.oracle_num_threads()

@@ -580,6 +580,74 @@ int oracle_merkle_par_frugal_root(const uint64_t *leafs, uint64_t n, uint64_t ro
     return rc;
 }
 
+/* MmrAccumulator::peaks_from_leafs for any leaf count (mmr/mmr_accumulator.rs:96-115); returns the number
+ * of peaks written (at most 64 digests). */
+uint64_t oracle_mmr_peaks_from_leafs(const uint64_t *leafs, uint64_t n, uint64_t *peaks) {
+    tip5_setup();
+    return peaks_from_leafs(leafs, n, peaks);
+}
+
+/* bag_peaks, mmr/mmr_accumulator.rs:379-391: hash_10 of the BFieldCodec encoding of leaf_count (two 32-bit
+ * limbs, bfield_codec.rs:122-128) padded with zeros, then folded from the last peak: acc = hash_pair(peak, acc) */
+void oracle_mmr_bag_peaks(const uint64_t *peaks, uint64_t n_peaks, uint64_t leaf_count, uint64_t out[5]) {
+    tip5_setup();
+    uint64_t in[10] = {0};
+    in[0] = bfe_new(leaf_count & 0xffffffffull);
+    in[1] = bfe_new(leaf_count >> 32);
+    uint64_t acc[5];
+    oracle_tip5_hash_10(in, acc);
+    for (uint64_t k = n_peaks; k-- > 0;) {
+        uint64_t next[5];
+        oracle_tip5_hash_pair(peaks + 5 * k, acc, next);
+        memcpy(acc, next, sizeof(acc));
+    }
+    memcpy(out, acc, sizeof(acc));
+}
+
+/* MerkleTree::authentication_structure_node_indices, merkle_tree.rs:449-504: the siblings along every
+ * leaf-to-root path that cannot be computed from the paths themselves, sorted by descending node index.
+ * out needs room for n_indices * log2(num_leafs) entries; returns the count or a negative error
+ * (-4 IncorrectNumberOfLeafs :467-469, -9 LeafIndexInvalid :487-489). */
+static int cmp_u64_desc(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? 1 : x > y ? -1 : 0;
+}
+static int cmp_u64_asc(const void *a, const void *b) { return -cmp_u64_desc(a, b); }
+int64_t oracle_auth_structure_node_indices(uint64_t num_leafs, const uint64_t *leaf_indices, uint64_t n_indices,
+                                           uint64_t *out) {
+    if (num_leafs == 0 || (num_leafs & (num_leafs - 1))) return ORACLE_E_INCORRECT_NUMBER_OF_LEAFS;
+    uint64_t height = 0;
+    while ((1ull << height) < num_leafs) height++;
+    uint64_t cap = n_indices * height + 1;
+    uint64_t *needed = (uint64_t *)malloc(sizeof(uint64_t) * cap);
+    uint64_t *computable = (uint64_t *)malloc(sizeof(uint64_t) * cap);
+    uint64_t nn = 0, nc = 0;
+    for (uint64_t k = 0; k < n_indices; k++) {
+        if (leaf_indices[k] >= num_leafs) {
+            free(needed);
+            free(computable);
+            return -9;
+        }
+        uint64_t node = leaf_indices[k] + num_leafs;
+        while (node > 1) {
+            computable[nc++] = node;
+            needed[nn++] = node ^ 1;
+            node /= 2;
+        }
+    }
+    qsort(needed, nn, sizeof(uint64_t), cmp_u64_desc);
+    qsort(computable, nc, sizeof(uint64_t), cmp_u64_asc);
+    int64_t count = 0;
+    for (uint64_t k = 0; k < nn; k++) {
+        if (k && needed[k] == needed[k - 1]) continue; /* set semantics */
+        if (bsearch(&needed[k], computable, nc, sizeof(uint64_t), cmp_u64_asc)) continue;
+        out[count++] = needed[k];
+    }
+    free(needed);
+    free(computable);
+    return count;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Field helpers exported for tests
  * ---------------------------------------------------------------------------------------- */

@@ -19,6 +19,7 @@ enum {
     ORACLE_E_TOO_FEW_LEAFS = -3,             /* MerkleTreeError::TooFewLeafs */
     ORACLE_E_INCORRECT_NUMBER_OF_LEAFS = -4, /* MerkleTreeError::IncorrectNumberOfLeafs */
     ORACLE_E_ORDER_LE_DEGREE = -5,           /* polynomial.rs:1388-1392 panic */
+    ORACLE_E_LEAF_INDEX_INVALID = -9,        /* MerkleTreeError::LeafIndexInvalid */
 };
 
 int oracle_ntt(uint64_t *x, uint64_t n, uint32_t w);
@@ -51,6 +52,11 @@ int oracle_merkle_par_new(const uint64_t *leafs, uint64_t n, uint64_t *nodes, in
 int oracle_merkle_sequential_frugal_root(const uint64_t *leafs, uint64_t n, uint64_t root[5]);
 int oracle_merkle_par_frugal_root(const uint64_t *leafs, uint64_t n, uint64_t root[5], int num_threads,
                                   uint64_t cutoff);
+
+uint64_t oracle_mmr_peaks_from_leafs(const uint64_t *leafs, uint64_t n, uint64_t *peaks /* <= 64 digests */);
+void oracle_mmr_bag_peaks(const uint64_t *peaks, uint64_t n_peaks, uint64_t leaf_count, uint64_t out[5]);
+int64_t oracle_auth_structure_node_indices(uint64_t num_leafs, const uint64_t *leaf_indices, uint64_t n_indices,
+                                           uint64_t *out);
 
 uint64_t oracle_bfe_new(uint64_t v);
 uint64_t oracle_bfe_value(uint64_t raw);

@@ -535,3 +535,68 @@ def test_poly_multiply_evaluation_property(tf, oracle):
     # zero polynomial
     z = tf.Polynomial(np.zeros(0, dtype=np.uint64)).fast_multiply(tf.Polynomial(a[:4].copy()))
     assert z.coefficients.size == 0
+
+
+# ---- next wave: authentication structures ------------------------------------------
+@pytest.mark.parametrize("height,k", [(0, 1), (1, 1), (3, 2), (6, 5), (10, 1), (10, 40), (14, 160), (18, 80)])
+def test_authentication_structure_matches_oracle(tf, oracle, height, k):
+    """merkle_tree.rs:514-542, 614-622: device-built tree + device gather == oracle tree indexed on the host"""
+    import torch
+
+    n = 1 << height
+    leafs = rnd(0x8000 + height, 5 * n)
+    rng = np.random.default_rng(height * 100 + k)
+    idx = rng.integers(0, n, size=k).astype(np.uint64)
+    rc, nodes = oracle.merkle_par_new(leafs)
+    assert rc == 0
+    rc, want_idx = oracle.auth_structure_node_indices(n, idx)
+    assert rc == 0
+    want = nodes.reshape(-1, 5)[want_idx.astype(np.int64)]
+    # host leaves in, host digests out
+    got = tf.MerkleTree.par_authentication_structure_from_leafs(leafs.reshape(n, 5), idx)
+    assert np.array_equal(got, want)
+    # host-resident tree (plain gather through the mirror)
+    tree = tf.MerkleTree.par_new(leafs.reshape(n, 5))
+    assert np.array_equal(tree.authentication_structure(idx), want)
+    # device-resident tree
+    d_leafs = torch.from_numpy(leafs.view(np.int64)).cuda()
+    d_nodes = torch.zeros(10 * n, dtype=torch.int64, device="cuda")
+    tf.device.merkle_build(d_leafs, d_nodes)
+    d_out = torch.zeros(5 * max(1, want.shape[0]), dtype=torch.int64, device="cuda")
+    cnt = tf.device.merkle_authentication_structure(d_nodes, idx, d_out)
+    assert cnt == want.shape[0]
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64)[: 5 * cnt].reshape(-1, 5), want)
+
+
+def test_authentication_structure_errors(tf):
+    leafs = np.zeros((8, 5), dtype=np.uint64)
+    with pytest.raises(tf.MerkleTreeError) as ei:
+        tf.MerkleTree.par_authentication_structure_from_leafs(leafs, [8])
+    assert ei.value.kind == "LeafIndexInvalid"
+    with pytest.raises(tf.MerkleTreeError) as ei:
+        tf.MerkleTree.par_authentication_structure_from_leafs(leafs[:6], [1])
+    assert ei.value.kind == "IncorrectNumberOfLeafs"
+    assert tf.MerkleTree.par_authentication_structure_from_leafs(leafs, []).shape == (0, 5)
+
+
+# ---- next wave (SURVEY.md 8f-4): MMR bulk operations ----------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7, 8, 11, 100, 255, 256, 257, 1000, 4097, (1 << 16) + 3, (1 << 18) - 1])
+def test_mmr_peaks_and_bag_peaks_match_oracle(tf, oracle, n):
+    """mmr_accumulator.rs:29-34, 96-115, 379-391 for arbitrary (non power of two) leaf counts"""
+    leafs = rnd(0x9000 + n, 5 * n)
+    want_peaks = oracle.mmr_peaks_from_leafs(leafs)
+    mmr = tf.MmrAccumulator.new_from_leafs(leafs.reshape(n, 5))
+    assert mmr.num_leafs() == n and mmr.is_consistent()
+    assert np.array_equal(mmr.peaks(), want_peaks)
+    assert np.array_equal(mmr.bag_peaks(), oracle.mmr_bag_peaks(want_peaks, n))
+
+
+def test_mmr_bag_peaks_reference_snapshot(tf, oracle):
+    """mmr_accumulator.rs:1038-1047 (empty MMR) and `init` with ten peaks and a 10-bit leaf count (:1061-1065)"""
+    empty = tf.MmrAccumulator.new_from_leafs(np.zeros((0, 5), dtype=np.uint64))
+    assert tf.Digest.to_hex(empty.bag_peaks()) == (
+        "cd65052100640f0d27e5654f97c47e49899add2f265967ccbefee7264e9bc08f588542d9dc3d5ac5")
+    peaks = rnd(0x9999, 50).reshape(10, 5)
+    for count in (0b11_1111_1111, (1 << 40) + 5, (1 << 64) - 1):
+        got = tf.MmrAccumulator(peaks, count).bag_peaks()
+        assert np.array_equal(got, oracle.mmr_bag_peaks(peaks, count))

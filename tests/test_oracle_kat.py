@@ -323,3 +323,65 @@ def test_poly_multiply_naive_equals_fast_and_doc_example(oracle):
     x2 = np.array([zero, zero, one], dtype=np.uint64)
     got = oracle.poly_naive_multiply(xx, x2, 3)
     assert [int(v) for v in oracle.to_values(got)] == [(1 << 64) - (1 << 32) + 1 - 1, 1, 0]
+
+
+# ---- next wave: authentication structures and MMR bulk operations ---------------
+def test_auth_structure_node_indices_reference_vectors(oracle):
+    """merkle_tree.rs:1594-1609 and the doc example :590-604"""
+    assert oracle.auth_structure_node_indices(8, [0, 1])[1].tolist() == [5, 3]
+    assert oracle.auth_structure_node_indices(8, [0, 2])[1].tolist() == [11, 9, 3]
+    assert oracle.auth_structure_node_indices(8, [4, 5, 6, 7])[1].tolist() == [2]
+    assert oracle.auth_structure_node_indices(8, [2])[1].tolist() == [11, 4, 3]
+    assert oracle.auth_structure_node_indices(8, [8])[0] == -9   # LeafIndexInvalid
+    assert oracle.auth_structure_node_indices(6, [0])[0] == -4   # IncorrectNumberOfLeafs
+    assert oracle.auth_structure_node_indices(1, [0])[1].tolist() == []
+
+
+def test_abi_auth_structure_node_indices_match_oracle_without_gpu(oracle):
+    """the index logic of the product is host code: same vectors + random cases, no device needed"""
+    import importlib
+
+    tf = importlib.import_module("twenty-first_b200")
+    assert tf.MerkleTree.authentication_structure_node_indices(8, [0, 2]).tolist() == [11, 9, 3]
+    rng = np.random.default_rng(7)
+    for height in (0, 1, 2, 5, 9, 16, 30):
+        n = 1 << height
+        for k in (0, 1, 2, 7, 40):
+            idx = rng.integers(0, n, size=k).astype(np.uint64)
+            rc, want = oracle.auth_structure_node_indices(n, idx)
+            assert rc == 0
+            assert np.array_equal(tf.MerkleTree.authentication_structure_node_indices(n, idx), want)
+    import pytest
+
+    with pytest.raises(tf.MerkleTreeError) as ei:
+        tf.MerkleTree.authentication_structure_node_indices(8, [8])
+    assert ei.value.kind == "LeafIndexInvalid"
+    with pytest.raises(tf.MerkleTreeError) as ei:
+        tf.MerkleTree.authentication_structure_node_indices(12, [1])
+    assert ei.value.kind == "IncorrectNumberOfLeafs"
+
+
+def test_mmr_bag_peaks_reference_snapshot_and_peak_structure(oracle):
+    """mmr_accumulator.rs:1038-1047: the snapshot of the empty MMR is the one vector that does not depend on
+    Rust's StdRng; peaks_from_leafs is checked structurally against the Merkle roots of the binary runs."""
+    empty = np.zeros(0, dtype=np.uint64)
+    assert oracle.digest_to_hex(oracle.mmr_bag_peaks(empty, 0)) == (
+        "cd65052100640f0d27e5654f97c47e49899add2f265967ccbefee7264e9bc08f588542d9dc3d5ac5")
+    for n in (0, 1, 2, 3, 5, 8, 11, 100, 255, 257):
+        leafs = __import__("oracle").splitmix64_words(0x7000 + n, 5 * n)
+        peaks = oracle.mmr_peaks_from_leafs(leafs)
+        assert peaks.shape[0] == bin(n).count("1")
+        off, k = 0, 0
+        for b in range(n.bit_length() - 1, -1, -1):
+            if (n >> b) & 1:
+                rc, root = oracle.merkle_sequential_frugal_root(leafs[5 * off: 5 * (off + (1 << b))])
+                assert rc == 0 and np.array_equal(peaks[k], root)
+                off += 1 << b
+                k += 1
+        # bag_peaks of a single-peak MMR = hash_pair(peak, hash_10(count, 0..))
+        if n and n & (n - 1) == 0:
+            cnt = np.zeros(10, dtype=np.uint64)
+            cnt[0] = oracle.bfe_new(n & 0xffffffff)
+            cnt[1] = oracle.bfe_new(n >> 32)
+            want = oracle.hash_pair(peaks[0].copy(), oracle.hash_10(cnt))
+            assert np.array_equal(oracle.mmr_bag_peaks(peaks, n), want)

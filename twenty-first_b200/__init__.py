@@ -10,8 +10,10 @@ Import with importlib (the directory name contains a hyphen):
 from ._binding import (  # noqa: F401
     E_ALLOC,
     E_BAD_ARG,
+    E_CAPACITY,
     E_CUDA,
     E_INCORRECT_NUMBER_OF_LEAFS,
+    E_LEAF_INDEX_INVALID,
     E_LEN_NOT_POW2,
     E_LEN_TOO_LARGE,
     E_ORDER_LE_DEGREE,
@@ -27,6 +29,7 @@ from .api import (  # noqa: F401
     Digest,
     MerkleTree,
     MerkleTreeError,
+    MmrAccumulator,
     Polynomial,
     Tip5,
     intt,

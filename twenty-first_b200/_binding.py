@@ -19,6 +19,8 @@ E_ORDER_LE_DEGREE = -5
 E_ALLOC = -6
 E_CUDA = -7
 E_BAD_ARG = -8
+E_LEAF_INDEX_INVALID = -9
+E_CAPACITY = -10
 
 u64 = ctypes.c_uint64
 u32 = ctypes.c_uint32
@@ -65,6 +67,13 @@ SIGNATURES = {
     "tf21_merkle_build_dev": (i32, [vp, u64, vp, vp]),
     "tf21_merkle_root_dev": (i32, [vp, u64, vp, vp]),
     "tf21_merkle_scatter_subtree_dev": (i32, [vp, u64, u64, u64, vp, vp]),
+    "tf21_merkle_auth_structure_node_indices": (i32, [u64, vp, u64, vp, u64, ctypes.POINTER(u64)]),
+    "tf21_merkle_authentication_structure_dev": (i32, [vp, u64, vp, u64, vp, u64, ctypes.POINTER(u64), vp]),
+    "tf21_merkle_authentication_structure_from_leafs": (i32, [vp, u64, vp, u64, vp, u64, ctypes.POINTER(u64)]),
+    "tf21_mmr_peaks_from_leafs": (i32, [vp, u64, vp, ctypes.POINTER(u64)]),
+    "tf21_mmr_peaks_from_leafs_dev": (i32, [vp, u64, vp, ctypes.POINTER(u64), vp]),
+    "tf21_mmr_bag_peaks": (i32, [vp, u64, u64, vp]),
+    "tf21_mmr_bag_peaks_dev": (i32, [vp, u64, u64, vp, vp]),
 }
 
 

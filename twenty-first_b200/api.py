@@ -7,6 +7,9 @@ Same names, argument meaning and error behaviour as the Rust crate:
   Tip5::{permutation, hash_10, hash_pair, hash_varlen}   tip5/mod.rs:529-623
   MerkleTree::{par_new, sequential_new, par_frugal_root, sequential_frugal_root, root, node,
                leafs, num_leafs, height}          util_types/merkle_tree.rs:149-364, 624-653
+  MerkleTree::{authentication_structure_node_indices, authentication_structure,
+               par_authentication_structure_from_leafs}   util_types/merkle_tree.rs:449-542, 614-622
+  MmrAccumulator::{new_from_leafs, peaks, bag_peaks}     util_types/mmr/mmr_accumulator.rs:29-34, 96-134, 379-391
 
 Arrays are numpy uint64 of *raw Montgomery words* -- exactly the bytes of a Rust
 `&[BFieldElement]` / `&[XFieldElement]` (width 3) / `&[Digest]` (5 words).  Where the reference
@@ -183,6 +186,7 @@ class MerkleTreeError(Exception):
     TOO_FEW_LEAFS = "TooFewLeafs"
     INCORRECT_NUMBER_OF_LEAFS = "IncorrectNumberOfLeafs"
     TREE_TOO_HIGH = "TreeTooHigh"
+    LEAF_INDEX_INVALID = "LeafIndexInvalid"
 
     def __init__(self, kind: str):
         self.kind = kind
@@ -196,6 +200,8 @@ def _merkle_check(code: int) -> None:
         raise MerkleTreeError(MerkleTreeError.INCORRECT_NUMBER_OF_LEAFS)
     if code == B.E_ALLOC:
         raise MerkleTreeError(MerkleTreeError.TREE_TOO_HIGH)
+    if code == B.E_LEAF_INDEX_INVALID:
+        raise MerkleTreeError(MerkleTreeError.LEAF_INDEX_INVALID)
     B.check(code)
 
 
@@ -248,3 +254,74 @@ class MerkleTree:
 
     def leafs(self) -> np.ndarray:  # :653
         return self.nodes[self.num_leafs():]
+
+    # ---- authentication structures ----------------------------------------
+    @staticmethod
+    def authentication_structure_node_indices(num_leafs: int, leaf_indices) -> np.ndarray:
+        """merkle_tree.rs:449-504: descending node indices; Err(IncorrectNumberOfLeafs / LeafIndexInvalid)"""
+        import ctypes
+
+        idx = np.ascontiguousarray(np.array(leaf_indices, dtype=np.uint64))
+        count = ctypes.c_uint64(0)
+        rc = B.lib.tf21_merkle_auth_structure_node_indices(num_leafs, _ptr(idx), idx.size, None, 0,
+                                                           ctypes.byref(count))
+        if rc != B.E_CAPACITY:
+            _merkle_check(rc)
+        out = np.zeros(count.value, dtype=np.uint64)
+        _merkle_check(B.lib.tf21_merkle_auth_structure_node_indices(num_leafs, _ptr(idx), idx.size, _ptr(out),
+                                                                    out.size, ctypes.byref(count)))
+        return out
+
+    def authentication_structure(self, leaf_indices) -> np.ndarray:
+        """merkle_tree.rs:614-622 on a host-resident node array: a plain gather"""
+        idx = MerkleTree.authentication_structure_node_indices(self.num_leafs(), leaf_indices)
+        return self.nodes[idx.astype(np.int64)]
+
+    @staticmethod
+    def par_authentication_structure_from_leafs(leafs: np.ndarray, leaf_indices) -> np.ndarray:
+        """merkle_tree.rs:532-542 (and the sequential form :514-523): tree built on the device, gathered there"""
+        import ctypes
+
+        leafs = _words(np.ascontiguousarray(leafs)).reshape(-1, 5)
+        idx = np.ascontiguousarray(np.array(leaf_indices, dtype=np.uint64))
+        need = MerkleTree.authentication_structure_node_indices(leafs.shape[0], idx).size
+        out = np.zeros((need, 5), dtype=np.uint64)
+        count = ctypes.c_uint64(0)
+        _merkle_check(B.lib.tf21_merkle_authentication_structure_from_leafs(
+            _ptr(leafs), leafs.shape[0], _ptr(idx), idx.size, _ptr(out), need, ctypes.byref(count)))
+        return out
+
+    sequential_authentication_structure_from_leafs = par_authentication_structure_from_leafs
+
+
+class MmrAccumulator:
+    """`MmrAccumulator` restricted to bulk construction and the commitment."""
+
+    def __init__(self, peaks: np.ndarray, leaf_count: int):  # `init`, mmr_accumulator.rs:25-27
+        self._peaks = np.ascontiguousarray(peaks, dtype=np.uint64).reshape(-1, 5)
+        self.leaf_count = int(leaf_count)
+
+    @staticmethod
+    def new_from_leafs(leafs: np.ndarray) -> "MmrAccumulator":
+        """mmr_accumulator.rs:29-34 / peaks_from_leafs :96-115; any leaf count including 0"""
+        import ctypes
+
+        leafs = _words(np.ascontiguousarray(leafs, dtype=np.uint64)).reshape(-1, 5)
+        peaks = np.zeros((64, 5), dtype=np.uint64)
+        n_peaks = ctypes.c_uint64(0)
+        B.check(B.lib.tf21_mmr_peaks_from_leafs(_ptr(leafs), leafs.shape[0], _ptr(peaks), ctypes.byref(n_peaks)))
+        return MmrAccumulator(peaks[: n_peaks.value].copy(), leafs.shape[0])
+
+    def peaks(self) -> np.ndarray:  # :133-135
+        return self._peaks
+
+    def num_leafs(self) -> int:  # :143-145
+        return self.leaf_count
+
+    def is_consistent(self) -> bool:  # :119-122
+        return self._peaks.shape[0] == bin(self.leaf_count).count("1")
+
+    def bag_peaks(self) -> np.ndarray:  # :127-129, 379-391
+        out = np.zeros(5, dtype=np.uint64)
+        B.check(B.lib.tf21_mmr_bag_peaks(_ptr(self._peaks), self._peaks.shape[0], self.leaf_count, _ptr(out)))
+        return out

@@ -1,6 +1,7 @@
 // tf21.cu -- the C ABI of libtf21 (include/tf21.h): argument checking, device state, host<->device
 // staging, and dispatch into the sm_100a kernels.  Single translation unit (the kernels live in the
 // included .cuh files) so the __constant__ tables are shared without relocatable device code.
+#include <algorithm>
 #include "ntt_fast.cuh"
 #include "tip5_kernels.cuh"
 
@@ -146,6 +147,8 @@ const char *tf21_strerror(int code) {
         case TF21_E_ALLOC: return "allocation failed (MerkleTreeError::TreeTooHigh)";
         case TF21_E_CUDA: return "CUDA error (see tf21_last_cuda_error)";
         case TF21_E_BAD_ARG: return "bad argument";
+        case TF21_E_LEAF_INDEX_INVALID: return "MerkleTreeError::LeafIndexInvalid";
+        case TF21_E_CAPACITY: return "output buffer too small";
         default: return "unknown tf21 error";
     }
 }
@@ -594,6 +597,157 @@ int tf21_merkle_scatter_subtree_dev(const uint64_t *d_local_nodes, uint64_t n_lo
     u64 total = (2 * n_local_leafs - 1) * 5;
     TF21_LAUNCH(merkle_scatter_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, d_local_nodes,
                 n_local_leafs, shard, n_shards, d_global_nodes);
+    return 0;
+}
+
+// Merkle root of d_leafs[0..n) into d_root_out using caller-provided scratch of 5*n words (n a power of two)
+static int merkle_root_with_scratch(const u64 *d_leafs, u64 n, u64 *d_root_out, u64 *scratch, cudaStream_t st) {
+    if (n == 1) {
+        TF21_CUDA(cudaMemcpyAsync(d_root_out, d_leafs, 5 * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    u64 cnt = n / 2;
+    TF21_TRY(launch_hash10(d_leafs, cnt, scratch + 5 * cnt, st));
+    if (cnt > 1) TF21_TRY(launch_merkle_levels(scratch, cnt, st));
+    TF21_CUDA(cudaMemcpyAsync(d_root_out, scratch + 5, 5 * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- next wave: authentication structures ------------------------------------------
+// merkle_tree.rs:449-504.  Host-side set logic: `needed` = siblings along every leaf-to-root path,
+// `computable` = the path nodes themselves; result = needed \ computable, descending.
+int tf21_merkle_auth_structure_node_indices(uint64_t n_leafs, const uint64_t *leaf_indices, uint64_t n_indices,
+                                            uint64_t *out, uint64_t capacity, uint64_t *count) {
+    if (n_leafs == 0 || (n_leafs & (n_leafs - 1))) return TF21_E_INCORRECT_NUMBER_OF_LEAFS;  // :467-469
+    if (!count || (n_indices && !leaf_indices)) return TF21_E_BAD_ARG;
+    std::vector<u64> needed, computable;
+    for (u64 k = 0; k < n_indices; k++) {
+        if (leaf_indices[k] >= n_leafs) return TF21_E_LEAF_INDEX_INVALID;  // :487-489
+        for (u64 node = leaf_indices[k] + n_leafs; node > 1; node >>= 1) {
+            computable.push_back(node);
+            needed.push_back(node ^ 1);
+        }
+    }
+    std::sort(needed.begin(), needed.end());
+    needed.erase(std::unique(needed.begin(), needed.end()), needed.end());
+    std::sort(computable.begin(), computable.end());
+    u64 c = 0;
+    for (auto it = needed.rbegin(); it != needed.rend(); ++it) {
+        if (std::binary_search(computable.begin(), computable.end(), *it)) continue;
+        if (c < capacity && out) out[c] = *it;
+        c++;
+    }
+    *count = c;
+    return (c > capacity || (c && !out)) ? TF21_E_CAPACITY : 0;
+}
+
+int tf21_merkle_authentication_structure_dev(const uint64_t *d_nodes, uint64_t n_leafs, const uint64_t *leaf_indices,
+                                             uint64_t n_indices, uint64_t *d_out, uint64_t capacity,
+                                             uint64_t *count, tf21_stream_t stream) {
+    if (!d_nodes || !count) return TF21_E_BAD_ARG;
+    u64 c = 0;
+    int rc = tf21_merkle_auth_structure_node_indices(n_leafs, leaf_indices, n_indices, nullptr, 0, &c);
+    if (rc != 0 && rc != TF21_E_CAPACITY) return rc;
+    *count = c;
+    if (c > capacity || (c && !d_out)) return TF21_E_CAPACITY;
+    if (c == 0) return 0;
+    std::vector<u64> idx(c);
+    TF21_TRY(tf21_merkle_auth_structure_node_indices(n_leafs, leaf_indices, n_indices, idx.data(), c, &c));
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch didx(st);
+    TF21_TRY(didx.alloc(c));
+    // pageable source: the copy is staged before cudaMemcpyAsync returns, so `idx` may go out of scope
+    TF21_CUDA(cudaMemcpyAsync(didx.p, idx.data(), c * sizeof(u64), cudaMemcpyHostToDevice, st));
+    TF21_LAUNCH(merkle_gather_kernel, grid_for(5 * c, 256), 256, 0, st, d_nodes, didx.p, c, d_out);
+    return 0;
+}
+
+// MerkleTree::{sequential,par}_authentication_structure_from_leafs (merkle_tree.rs:514-542): the reference
+// computes one frugal root per needed node; here the tree is built once on the device and gathered from.
+int tf21_merkle_authentication_structure_from_leafs(const uint64_t *leafs, uint64_t n_leafs,
+                                                    const uint64_t *leaf_indices, uint64_t n_indices,
+                                                    uint64_t *out, uint64_t capacity, uint64_t *count) {
+    if (!count) return TF21_E_BAD_ARG;
+    u64 c = 0;
+    int rc = tf21_merkle_auth_structure_node_indices(n_leafs, leaf_indices, n_indices, nullptr, 0, &c);
+    if (rc != 0 && rc != TF21_E_CAPACITY) return rc;
+    *count = c;
+    if (c > capacity || (c && !out)) return TF21_E_CAPACITY;
+    if (c == 0) return 0;
+    if (!leafs) return TF21_E_BAD_ARG;
+    DevBuf bl, bn, bo;
+    TF21_TRY(bl.alloc(5 * n_leafs));
+    TF21_TRY(bn.alloc(10 * n_leafs));
+    TF21_TRY(bo.alloc(5 * c));
+    TF21_CUDA(cudaMemcpy(bl.p, leafs, 5 * n_leafs * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_merkle_build_dev(bl.p, n_leafs, bn.p, nullptr));
+    TF21_TRY(tf21_merkle_authentication_structure_dev(bn.p, n_leafs, leaf_indices, n_indices, bo.p, c, &c, nullptr));
+    TF21_CUDA(cudaMemcpy(out, bo.p, 5 * c * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- next wave: MMR bulk operations -------------------------------------------------
+// MmrAccumulator::peaks_from_leafs (mmr/mmr_accumulator.rs:96-115): the peaks are the Merkle roots of the
+// power-of-two runs of the binary expansion of n_leafs, most significant first; an odd count leaves the
+// last leaf as its own peak.  Each run is one level-batched build.
+int tf21_mmr_peaks_from_leafs_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d_peaks_out,
+                                  uint64_t *n_peaks, tf21_stream_t stream) {
+    if (!n_peaks) return TF21_E_BAD_ARG;
+    *n_peaks = (u64)__builtin_popcountll(n_leafs);
+    if (n_leafs == 0) return 0;
+    if (!d_leafs || !d_peaks_out) return TF21_E_BAD_ARG;
+    if (n_leafs > (1ull << 40)) return TF21_E_ALLOC;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned top = ilog2_u64(n_leafs);
+    Scratch scratch(st);
+    if (top >= 1) TF21_TRY(scratch.alloc(5ull << top));
+    u64 off = 0, k = 0;
+    for (int b = (int)top; b >= 0; b--) {
+        if (!((n_leafs >> b) & 1)) continue;
+        TF21_TRY(merkle_root_with_scratch(d_leafs + 5 * off, 1ull << b, d_peaks_out + 5 * k, scratch.p, st));
+        off += 1ull << b;
+        k++;
+    }
+    return 0;
+}
+
+int tf21_mmr_peaks_from_leafs(const uint64_t *leafs, uint64_t n_leafs, uint64_t *peaks_out, uint64_t *n_peaks) {
+    if (!n_peaks) return TF21_E_BAD_ARG;
+    *n_peaks = (u64)__builtin_popcountll(n_leafs);
+    if (n_leafs == 0) return 0;
+    if (!leafs || !peaks_out) return TF21_E_BAD_ARG;
+    DevBuf bl, bp;
+    TF21_TRY(bl.alloc(5 * n_leafs));
+    TF21_TRY(bp.alloc(5 * 64));
+    TF21_CUDA(cudaMemcpy(bl.p, leafs, 5 * n_leafs * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_mmr_peaks_from_leafs_dev(bl.p, n_leafs, bp.p, n_peaks, nullptr));
+    TF21_CUDA(cudaMemcpy(peaks_out, bp.p, 5 * *n_peaks * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tf21_mmr_bag_peaks_dev(const uint64_t *d_peaks, uint64_t n_peaks, uint64_t leaf_count, uint64_t *d_out,
+                           tf21_stream_t stream) {
+    if (!d_out || (n_peaks && !d_peaks) || n_peaks > 64) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    // BFieldCodec of u64: two 32-bit limbs, low first (bfield_codec.rs:122-128)
+    const u64 lo = hgl_to_raw(leaf_count & 0xffffffffull), hi = hgl_to_raw(leaf_count >> 32);
+    TF21_LAUNCH(mmr_bag_peaks_kernel, 1, 32, 0, (cudaStream_t)stream, d_peaks, (u32)n_peaks, lo, hi, d_out);
+    return 0;
+}
+
+int tf21_mmr_bag_peaks(const uint64_t *peaks, uint64_t n_peaks, uint64_t leaf_count, uint64_t out[5]) {
+    if (!out || (n_peaks && !peaks) || n_peaks > 64) return TF21_E_BAD_ARG;
+    DevBuf bp, bo;
+    TF21_TRY(bp.alloc(5 * n_peaks));
+    TF21_TRY(bo.alloc(5));
+    if (n_peaks) TF21_CUDA(cudaMemcpy(bp.p, peaks, 5 * n_peaks * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_mmr_bag_peaks_dev(bp.p, n_peaks, leaf_count, bo.p, nullptr));
+    TF21_CUDA(cudaMemcpy(out, bo.p, 5 * sizeof(u64), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -92,6 +92,9 @@ inline int upload_tip5_constants() {
 }
 
 constexpr int kTip5Threads = 128;
+#ifndef TIP5_MIN_BLOCKS
+#define TIP5_MIN_BLOCKS 4  /* resident CTAs per SM the register allocation aims for (A/B: tools/ab.sh) */
+#endif
 
 // in-place permutation of `count` 16-word states (Tip5::permutation, tip5/mod.rs:529-533)
 __global__ void __launch_bounds__(kTip5Threads) tip5_permute_kernel(u64 *__restrict__ states, u64 count) {
@@ -114,9 +117,12 @@ __global__ void __launch_bounds__(kTip5Threads) tip5_permute_kernel(u64 *__restr
     for (int k = 0; k < 8; k++) dst[k] = make_ulonglong2(gl_canon(s[2 * k]), gl_canon(s[2 * k + 1]));
 }
 
-// Tip5::hash_10 / hash_pair over a batch (tip5/mod.rs:559-586): state = in[0..10) | ONE x 6
-__global__ void __launch_bounds__(kTip5Threads)
-    tip5_hash10_kernel(const u64 *__restrict__ in, u64 count, u64 *__restrict__ out) {
+// Tip5::hash_10 / hash_pair over a batch (tip5/mod.rs:559-586): state = in[0..10) | ONE x 6.
+// COPY: also store the 10 input words at copy_dst + 10 i -- the leaf level of the Merkle build, where the
+// reference copies the leaves into the node array (merkle_tree.rs:426) before hashing them.
+template <bool COPY>
+__global__ void __launch_bounds__(kTip5Threads, TIP5_MIN_BLOCKS)
+    tip5_hash10_kernel(const u64 *__restrict__ in, u64 count, u64 *__restrict__ out, u64 *__restrict__ copy_dst) {
     __shared__ uint8_t s_lut[256];
     tip5_load_lut(s_lut);
     __syncthreads();
@@ -129,6 +135,7 @@ __global__ void __launch_bounds__(kTip5Threads)
         ulonglong2 v = src[k];
         s[2 * k] = v.x;
         s[2 * k + 1] = v.y;
+        if (COPY) reinterpret_cast<ulonglong2 *>(copy_dst + 10 * i)[k] = v;
     }
     tip5_permutation<true>(s, s_lut);  // capacity lanes = ONE, folded into the round-0 constants
     u64 *dst = out + 5 * i;
@@ -216,6 +223,43 @@ __global__ void merkle_scatter_kernel(const u64 *__restrict__ local, u64 n_local
     global[5 * g + lane] = local[5 * node + lane];
 }
 
+// out[k] = nodes[idx[k]]: the gather behind MerkleTree::authentication_structure (merkle_tree.rs:614-622);
+// one thread per word of the result
+__global__ void merkle_gather_kernel(const u64 *__restrict__ nodes, const u64 *__restrict__ idx, u64 count,
+                                     u64 *__restrict__ out) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 5 * count) return;
+    out[t] = nodes[5 * idx[t / 5] + t % 5];
+}
+
+// bag_peaks (mmr/mmr_accumulator.rs:379-391): a sequential chain of at most 65 hashes -- one thread.
+// acc = hash_10(lo32(leaf_count), hi32(leaf_count), 0 x 8) (raw words passed in by the host), then from the
+// last peak to the first: acc = hash_pair(peak, acc).
+__global__ void __launch_bounds__(32) mmr_bag_peaks_kernel(const u64 *__restrict__ peaks, u32 n_peaks, u64 lc_lo_raw,
+                                                           u64 lc_hi_raw, u64 *__restrict__ out) {
+    __shared__ uint8_t s_lut[256];
+    tip5_load_lut(s_lut);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    u64 s[TIP5_STATE];
+    s[0] = lc_lo_raw;
+    s[1] = lc_hi_raw;
+#pragma unroll
+    for (int k = 2; k < TIP5_RATE; k++) s[k] = 0;
+    tip5_permutation<true>(s, s_lut);
+#pragma unroll 1
+    for (u32 k = n_peaks; k-- > 0;) {
+#pragma unroll
+        for (int j = 0; j < TIP5_DIGEST; j++) {
+            s[TIP5_DIGEST + j] = gl_canon(s[j]);
+            s[j] = peaks[5 * k + j];
+        }
+        tip5_permutation<true>(s, s_lut);
+    }
+#pragma unroll
+    for (int j = 0; j < TIP5_DIGEST; j++) out[j] = gl_canon(s[j]);
+}
+
 inline unsigned grid_for(u64 count, int threads) { return (unsigned)((count + threads - 1) / threads); }
 
 inline int launch_permute(u64 *d_states, u64 count, cudaStream_t st) {
@@ -226,7 +270,16 @@ inline int launch_permute(u64 *d_states, u64 count, cudaStream_t st) {
 
 inline int launch_hash10(const u64 *d_in, u64 count, u64 *d_out, cudaStream_t st) {
     if (count == 0) return 0;
-    TF21_LAUNCH(tip5_hash10_kernel, grid_for(count, kTip5Threads), kTip5Threads, 0, st, d_in, count, d_out);
+    TF21_LAUNCH_NAMED("tip5_hash10_kernel", tip5_hash10_kernel<false>, grid_for(count, kTip5Threads), kTip5Threads, 0,
+                      st, d_in, count, d_out, (u64 *)nullptr);
+    return 0;
+}
+
+// leaf level of a Merkle build: hash the pairs of d_leafs into d_out and copy the leaves to d_copy
+inline int launch_hash10_copy(const u64 *d_in, u64 count, u64 *d_out, u64 *d_copy, cudaStream_t st) {
+    if (count == 0) return 0;
+    TF21_LAUNCH_NAMED("tip5_hash10_kernel", tip5_hash10_kernel<true>, grid_for(count, kTip5Threads), kTip5Threads, 0,
+                      st, d_in, count, d_out, d_copy);
     return 0;
 }
 
@@ -263,9 +316,15 @@ inline int check_leaf_count(u64 n) {
 inline int merkle_build_dev(const u64 *d_leafs, u64 n, u64 *d_nodes, cudaStream_t st) {
     TF21_TRY(check_leaf_count(n));
     u64 words = 5 * n;
-    unsigned grid = (unsigned)std::min<u64>((words + 255) / 256, 148 * 16);
-    TF21_LAUNCH(merkle_init_kernel, grid, 256, 0, st, d_leafs, words, d_nodes);
-    return launch_merkle_levels(d_nodes, n, st);
+    if (n < 2 * (u64)kMerkleTailCnt) {  // small trees: copy, then the single-CTA tail
+        unsigned grid = (unsigned)std::min<u64>((words + 255) / 256, 148 * 16);
+        TF21_LAUNCH(merkle_init_kernel, grid, 256, 0, st, d_leafs, words, d_nodes);
+        return launch_merkle_levels(d_nodes, n, st);
+    }
+    // nodes[0] = 0; the leaf level copies the leaves into nodes[n..2n) while hashing them (one read of the leaves)
+    TF21_CUDA(cudaMemsetAsync(d_nodes, 0, 5 * sizeof(u64), st));
+    TF21_TRY(launch_hash10_copy(d_leafs, n / 2, d_nodes + 5 * (n / 2), d_nodes + words, st));
+    return launch_merkle_levels(d_nodes, n / 2, st);
 }
 
 }  // namespace tf21

@@ -72,6 +72,32 @@ def merkle_scatter_subtree(local_nodes: torch.Tensor, shard: int, n_shards: int,
                                                   _p(global_nodes), _stream()))
 
 
+def merkle_authentication_structure(nodes: torch.Tensor, leaf_indices, out: torch.Tensor) -> int:
+    """out[k] = nodes[needed index k] (MerkleTree::authentication_structure); returns the digest count"""
+    import ctypes
+
+    import numpy as np
+
+    idx = np.ascontiguousarray(np.array(leaf_indices, dtype=np.uint64))
+    count = ctypes.c_uint64(0)
+    B.check(B.lib.tf21_merkle_authentication_structure_dev(_p(nodes), nodes.numel() // 10, idx.ctypes.data if idx.size else None,
+                                                           idx.size, _p(out), out.numel() // 5, ctypes.byref(count),
+                                                           _stream()))
+    return int(count.value)
+
+
+def mmr_peaks_from_leafs(leafs: torch.Tensor, peaks: torch.Tensor) -> int:
+    import ctypes
+
+    n_peaks = ctypes.c_uint64(0)
+    B.check(B.lib.tf21_mmr_peaks_from_leafs_dev(_p(leafs), leafs.numel() // 5, _p(peaks), ctypes.byref(n_peaks), _stream()))
+    return int(n_peaks.value)
+
+
+def mmr_bag_peaks(peaks: torch.Tensor, leaf_count: int, out: torch.Tensor) -> None:
+    B.check(B.lib.tf21_mmr_bag_peaks_dev(_p(peaks), peaks.numel() // 5, leaf_count, _p(out), _stream()))
+
+
 def kernel_launch_count() -> int:
     return int(B.lib.tf21_kernel_launch_count())
 
