@@ -33,6 +33,10 @@ typedef uint32_t u32;
 #define TF21_SUB_WIDE 0  /* measured -3 %: the FMA pipe is as loaded as the ALU pipe */
 #endif
 
+#ifndef TF21_MUL_WIDE_LOW
+#define TF21_MUL_WIDE_LOW 1
+#endif
+
 #ifdef __CUDACC__
 
 // 2^t as an operand ptxas cannot see through (a __constant__ may be rewritten by the host), so that
@@ -187,6 +191,152 @@ __device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {
 #else
     return gl_reduce128(r0, r1, r2, r3);
 #endif
+}
+
+// ---- ALU-only Solinas folds for FMA-pipe-bound code (Tip5) --------------------------------------------
+// In the Tip5 round the FMA-heavy pipe is the busiest (48 modular products = 192 IMAD.WIDE at one warp
+// instruction per 5.3 cycles, ~78 % busy) while the ALU pipe is at ~45 %.  The r2 * EPS term of the folds above
+// costs one IMAD + one IMAD.HI (7.3 FMA-pipe cycles); here it is built on the ALU as the 64-bit difference
+// (r2 << 32) - r2 = (-r2, r2 - (r2 != 0)) and added with carry: 4 ALU instructions, no multiply.
+#ifndef TF21_EPS_NOT
+#define TF21_EPS_NOT 0
+#endif
+#if TF21_EPS_NOT  /* (~r2 + 1, r2 + 0xffffffff + carry): one more LOP3, no negate on the FMA pipe */
+#define GL_EPS_TERM(R) "not.b32 n2," R ";\n\tadd.cc.u32 tl,n2,1;\n\taddc.u32 th," R ",0xffffffff;\n\t"
+#else
+#define GL_EPS_TERM(R) "sub.cc.u32 tl,0," R ";\n\tsubc.u32 th," R ",0;\n\t"
+#endif
+__device__ __forceinline__ u64 gl_reduce96a(u64 x0, u32 x1) {  // x0 + x1 2^64 -> any u64
+    u64 out;
+    asm("{\n\t.reg .u32 lo,hi,c,tl,th,n2; .reg .pred p; .reg .u64 v;\n\t"
+        "mov.b64 {lo,hi},%1;\n\t"
+        GL_EPS_TERM("%2")
+        "add.cc.u32 lo,lo,tl;\n\t"
+        "addc.cc.u32 hi,hi,th;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.eq.u32 p,c,0;\n\t"
+        "mov.b64 v,{lo,hi};\n\t"
+        "@p bra GLNA%=;\n\t"
+        "add.u64 v,v,0xffffffff;\n\t"
+        "GLNA%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(out)
+        : "l"(x0), "r"(x1));
+    return out;
+}
+
+__device__ __forceinline__ u64 gl_reduce128a(u32 r0, u32 r1, u32 r2, u32 r3) {
+    u64 out;
+    asm("{\n\t.reg .u32 lo,hi,c,d,n3,tl,th,n2; .reg .pred p; .reg .u64 v;\n\t"
+        "not.b32 n3,%4;\n\t"
+        "add.cc.u32 d,0xffffffff,1;\n\t"
+        "addc.cc.u32 lo,%1,n3;\n\t"
+        "addc.cc.u32 hi,%2,0xffffffff;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.ne.u32 p,c,0;\n\t"
+        "mov.b64 v,{lo,hi};\n\t"
+        "@p bra GLRA1%=;\n\t"
+        "sub.u64 v,v,0xffffffff;\n\t"
+        "GLRA1%=:\n\t"
+        "mov.b64 {lo,hi},v;\n\t"
+        GL_EPS_TERM("%3")
+        "add.cc.u32 lo,lo,tl;\n\t"
+        "addc.cc.u32 hi,hi,th;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.eq.u32 p,c,0;\n\t"
+        "mov.b64 v,{lo,hi};\n\t"
+        "@p bra GLRA2%=;\n\t"
+        "add.u64 v,v,0xffffffff;\n\t"
+        "GLRA2%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(out)
+        : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
+    return out;
+}
+
+// 64x64 -> 128 with the low product as one mul.wide (ptxas keeps mul.lo + mul.hi as IMAD + IMAD.HI)
+__device__ __forceinline__ void gl_mul128w(u64 a, u64 b, u32 &r0, u32 &r1, u32 &r2, u32 &r3) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    asm("{\n\t.reg .u64 t;\n\t"
+        "mul.wide.u32 t,%4,%6;\n\t"
+        "mov.b64 {%0,%1},t;\n\t"
+        "mad.lo.cc.u32 %1,%4,%7,%1;\n\t"
+        "madc.hi.u32 %2,%4,%7,0;\n\t"
+        "mad.lo.cc.u32 %1,%5,%6,%1;\n\t"
+        "madc.hi.cc.u32 %2,%5,%6,%2;\n\t"
+        "addc.u32 %3,0,0;\n\t"
+        "mad.lo.cc.u32 %2,%5,%7,%2;\n\t"
+        "madc.hi.u32 %3,%5,%7,%3;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+
+// 64x64 -> 128 as four plain wide multiplies (4.2 cycles each, against 5.3 for the multiply-add with a 64-bit
+// addend) + 6 full-rate additions (tools/ubench3.cu)
+__device__ __forceinline__ void gl_mul128_nw(u64 a, u64 b, u32 &r0, u32 &r1, u32 &r2, u32 &r3) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    asm("{\n\t.reg .u64 p00,p01,p10,p11; .reg .u32 l1,h1,l2,h2;\n\t"
+        "mul.wide.u32 p00,%4,%6;\n\t"
+        "mul.wide.u32 p01,%4,%7;\n\t"
+        "mul.wide.u32 p10,%5,%6;\n\t"
+        "mul.wide.u32 p11,%5,%7;\n\t"
+        "mov.b64 {%0,%1},p00;\n\t"
+        "mov.b64 {%2,%3},p11;\n\t"
+        "mov.b64 {l1,h1},p01;\n\t"
+        "mov.b64 {l2,h2},p10;\n\t"
+        "add.cc.u32 %1,%1,l1;\n\t"
+        "addc.cc.u32 %2,%2,h1;\n\t"
+        "addc.u32 %3,%3,0;\n\t"
+        "add.cc.u32 %1,%1,l2;\n\t"
+        "addc.cc.u32 %2,%2,h2;\n\t"
+        "addc.u32 %3,%3,0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ u64 gl_mul_nw(u64 a, u64 b) {
+    u32 r0, r1, r2, r3;
+    gl_mul128_nw(a, b, r0, r1, r2, r3);
+    return gl_reduce128p(r0, r1, r2, r3);
+}
+
+// x^2 mod p with three 32x32 products instead of four: x^2 = x0^2 + 2 x0 x1 2^32 + x1^2 2^64; the doubled cross
+// product is formed by adding it twice into the 96-bit window (x0^2 >> 32 | x1^2 << 32) -- 3 wide multiplies
+// (quarter rate: 4.2 cycles per warp instruction) + 6 full-rate additions instead of 1 + 3 multiply-adds.
+__device__ __forceinline__ u64 gl_sqr(u64 x) {
+    u32 x0 = (u32)x, x1 = (u32)(x >> 32);
+    u32 r0, r1, r2, r3;
+    asm("{\n\t.reg .u64 p00,p01,p11; .reg .u32 m0,m1;\n\t"
+        "mul.wide.u32 p00,%4,%4;\n\t"
+        "mul.wide.u32 p01,%4,%5;\n\t"
+        "mul.wide.u32 p11,%5,%5;\n\t"
+        "mov.b64 {%0,%1},p00;\n\t"
+        "mov.b64 {%2,%3},p11;\n\t"
+        "mov.b64 {m0,m1},p01;\n\t"
+        "add.cc.u32 %1,%1,m0;\n\t"
+        "addc.cc.u32 %2,%2,m1;\n\t"
+        "addc.u32 %3,%3,0;\n\t"
+        "add.cc.u32 %1,%1,m0;\n\t"
+        "addc.cc.u32 %2,%2,m1;\n\t"
+        "addc.u32 %3,%3,0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(x0), "r"(x1));
+    return gl_reduce128p(r0, r1, r2, r3);
+}
+
+// a * b mod p for Tip5's S-box: same value as gl_mul, reduction on the ALU pipe
+__device__ __forceinline__ u64 gl_mul_alu(u64 a, u64 b) {
+    u32 r0, r1, r2, r3;
+#if TF21_MUL_WIDE_LOW
+    gl_mul128w(a, b, r0, r1, r2, r3);
+#else
+    gl_mul128(a, b, r0, r1, r2, r3);
+#endif
+    return gl_reduce128a(r0, r1, r2, r3);
 }
 
 // canonical product

@@ -24,6 +24,28 @@
 #ifndef TIP5_MDS_CRT
 #define TIP5_MDS_CRT 1  /* MDS as cyclic-8 + negacyclic-8 products (CRT over x^16 - 1): 320 instead of 512 FP64 ops per round */
 #endif
+#ifndef TIP5_ALU_FOLD
+#define TIP5_ALU_FOLD 0  /* Solinas folds of the S-box products and the MDS outputs on the ALU pipe (field.cuh): measured +1 % time */
+#endif
+#ifndef TIP5_SQR
+#define TIP5_SQR 1  /* the two squarings of x^7 with three wide multiplies (gl_sqr) */
+#endif
+#ifndef TIP5_MDS_SPLIT
+#define TIP5_MDS_SPLIT 1
+#endif
+#ifndef TIP5_MUL_NW
+#define TIP5_MUL_NW 0
+#endif
+#if TIP5_MUL_NW
+#define TIP5_MUL gl_mul_nw
+#define TIP5_REDUCE96 gl_reduce96
+#elif TIP5_ALU_FOLD
+#define TIP5_MUL gl_mul_alu
+#define TIP5_REDUCE96 gl_reduce96a
+#else
+#define TIP5_MUL gl_mul
+#define TIP5_REDUCE96 gl_reduce96
+#endif
 #define TIP5_STATE 16
 #define TIP5_RATE 10
 #define TIP5_ROUNDS 5
@@ -78,13 +100,65 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
 #pragma unroll
     for (int i = 4; i < NVAR; i++) {
         u64 x = s[i];
-        u64 x2 = gl_mul(x, x);
-        u64 x4 = gl_mul(x2, x2);
-        u64 x6 = gl_mul(x2, x4);
-        s[i] = gl_mul(x, x6);
+#if TIP5_SQR
+        u64 x2 = gl_sqr(x);
+        u64 x4 = gl_sqr(x2);
+#else
+        u64 x2 = TIP5_MUL(x, x);
+        u64 x4 = TIP5_MUL(x2, x2);
+#endif
+        u64 x6 = TIP5_MUL(x2, x4);
+        s[i] = TIP5_MUL(x, x6);
     }
     // ---- MDS + round constants (exact integer arithmetic on the FP64 pipe) ----
     const double kBias = 4503599627370496.0;  // 2^52
+#if TIP5_MDS_CRT && TIP5_MDS_SPLIT
+    // Same CRT products as below, but the low 32-bit halves of all lanes first, then the high halves: 16 + 16
+    // doubles live instead of 64, which is what lets the register allocation fit one more CTA per SM.
+    u64 acc_l[TIP5_STATE];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        double a[8], b[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double x = __uint2double_rn(h ? (u32)(s[j] >> 32) : (u32)s[j]);
+            if (j + 8 < NVAR) {
+                const double y = __uint2double_rn(h ? (u32)(s[j + 8] >> 32) : (u32)s[j + 8]);
+                a[j] = x + y;
+                b[j] = x - y;
+            } else {
+                a[j] = b[j] = x;
+            }
+        }
+        const double *rc = h ? rc_hi : rc_lo;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            double p = rc[i], q = rc[8 + i];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k = (i - j) & 7;
+                const double mp = 0.5 * ((double)TIP5_MDS(k) + (double)TIP5_MDS(k + 8));
+                const double mn = (j <= i ? 0.5 : -0.5) * ((double)TIP5_MDS(k) - (double)TIP5_MDS(k + 8));
+                p = fma(mp, a[j], p);
+                q = fma(mn, b[j], q);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const u64 acc = __double2ull_rn(half ? p - q : p + q);
+                if (h == 0) {
+                    acc_l[i + 8 * half] = acc;
+                } else {
+                    const u64 acc_lo = acc_l[i + 8 * half];
+                    u64 x0 = acc_lo + (acc << 32);
+                    u32 x1 = (u32)(acc >> 32) + (x0 < acc_lo ? 1u : 0u);
+                    const u64 v = TIP5_REDUCE96(x0, x1);
+                    s[i + 8 * half] = (i + 8 * half < 4) ? gl_canon(v) : v;
+                }
+            }
+        }
+    }
+    return;
+#endif
     double dl[NVAR], dh[NVAR];
 #pragma unroll
     for (int j = 0; j < NVAR; j++) {
@@ -143,7 +217,7 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
 #endif
             u64 x0 = acc_lo + (acc_hi << 32);
             u32 x1 = (u32)(acc_hi >> 32) + (x0 < acc_lo ? 1u : 0u);
-            const u64 v = gl_reduce96(x0, x1);
+            const u64 v = TIP5_REDUCE96(x0, x1);
             s[i + 8 * half] = (i + 8 * half < 4) ? gl_canon(v) : v;
         }
     }
