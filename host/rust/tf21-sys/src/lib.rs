@@ -14,6 +14,8 @@ pub const TF21_E_ORDER_LE_DEGREE: c_int = -5;
 pub const TF21_E_ALLOC: c_int = -6;
 pub const TF21_E_CUDA: c_int = -7;
 pub const TF21_E_BAD_ARG: c_int = -8;
+pub const TF21_E_LEAF_INDEX_INVALID: c_int = -9;
+pub const TF21_E_CAPACITY: c_int = -10;
 
 pub type tf21_stream_t = *mut c_void; // cudaStream_t
 
@@ -70,4 +72,19 @@ extern "C" {
     pub fn tf21_merkle_root_dev(leafs: *const u64, n_leafs: u64, root_out: *mut u64, s: tf21_stream_t) -> c_int;
     pub fn tf21_merkle_scatter_subtree_dev(local_nodes: *const u64, n_local_leafs: u64, shard: u64, n_shards: u64,
                                            global_nodes: *mut u64, s: tf21_stream_t) -> c_int;
+
+    pub fn tf21_merkle_auth_structure_node_indices(n_leafs: u64, leaf_indices: *const u64, n_indices: u64,
+                                                   out: *mut u64, capacity: u64, count: *mut u64) -> c_int;
+    pub fn tf21_merkle_authentication_structure_dev(nodes: *const u64, n_leafs: u64, leaf_indices: *const u64,
+                                                    n_indices: u64, out: *mut u64, capacity: u64, count: *mut u64,
+                                                    s: tf21_stream_t) -> c_int;
+    pub fn tf21_merkle_authentication_structure_from_leafs(leafs: *const u64, n_leafs: u64, leaf_indices: *const u64,
+                                                           n_indices: u64, out: *mut u64, capacity: u64,
+                                                           count: *mut u64) -> c_int;
+    pub fn tf21_mmr_peaks_from_leafs(leafs: *const u64, n_leafs: u64, peaks_out: *mut u64, n_peaks: *mut u64) -> c_int;
+    pub fn tf21_mmr_peaks_from_leafs_dev(leafs: *const u64, n_leafs: u64, peaks_out: *mut u64, n_peaks: *mut u64,
+                                         s: tf21_stream_t) -> c_int;
+    pub fn tf21_mmr_bag_peaks(peaks: *const u64, n_peaks: u64, leaf_count: u64, out: *mut u64) -> c_int;
+    pub fn tf21_mmr_bag_peaks_dev(peaks: *const u64, n_peaks: u64, leaf_count: u64, out: *mut u64,
+                                  s: tf21_stream_t) -> c_int;
 }

@@ -118,6 +118,7 @@ fn merkle_err(code: i32) -> MerkleTreeError {
         sys::TF21_E_TOO_FEW_LEAFS => MerkleTreeError::TooFewLeafs,
         sys::TF21_E_INCORRECT_NUMBER_OF_LEAFS => MerkleTreeError::IncorrectNumberOfLeafs,
         sys::TF21_E_ALLOC => MerkleTreeError::TreeTooHigh,
+        sys::TF21_E_LEAF_INDEX_INVALID => MerkleTreeError::LeafIndexInvalid,
         other => fail(other),
     }
 }
@@ -146,4 +147,58 @@ pub fn merkle_frugal_root(leafs: &[Digest]) -> Result<Digest, MerkleTreeError> {
         return Err(merkle_err(rc));
     }
     Ok(root)
+}
+
+/// MerkleTree::par_authentication_structure_from_leafs / sequential_… (merkle_tree.rs:514-542): the tree is
+/// built once on the device and the needed nodes are gathered there (the reference computes one frugal root
+/// per needed node); same digests, same (descending node index) order.
+pub fn authentication_structure_from_leafs(leafs: &[Digest], leaf_indices: &[usize]) -> Result<Vec<Digest>, MerkleTreeError> {
+    let idx: Vec<u64> = leaf_indices.iter().map(|&i| i as u64).collect();
+    let mut count = 0u64;
+    let rc = unsafe {
+        sys::tf21_merkle_auth_structure_node_indices(leafs.len() as u64, idx.as_ptr(), idx.len() as u64,
+                                                     core::ptr::null_mut(), 0, &mut count)
+    };
+    if rc != 0 && rc != sys::TF21_E_CAPACITY {
+        return Err(merkle_err(rc));
+    }
+    let mut out = vec![Digest::default(); count as usize];
+    let rc = unsafe {
+        sys::tf21_merkle_authentication_structure_from_leafs(leafs.as_ptr() as *const u64, leafs.len() as u64,
+                                                             idx.as_ptr(), idx.len() as u64,
+                                                             out.as_mut_ptr() as *mut u64, count, &mut count)
+    };
+    if rc != 0 {
+        return Err(merkle_err(rc));
+    }
+    Ok(out)
+}
+
+/// MmrAccumulator::new_from_leafs -> (peaks, leaf_count) (mmr/mmr_accumulator.rs:29-34, 96-115); any leaf count.
+/// `MmrAccumulator::init(peaks, leaf_count)` (:25-27) turns the pair into the reference's struct.
+pub fn mmr_peaks_from_leafs(leafs: &[Digest]) -> Vec<Digest> {
+    let mut peaks = vec![Digest::default(); 64];
+    let mut n_peaks = 0u64;
+    let rc = unsafe {
+        sys::tf21_mmr_peaks_from_leafs(leafs.as_ptr() as *const u64, leafs.len() as u64,
+                                       peaks.as_mut_ptr() as *mut u64, &mut n_peaks)
+    };
+    if rc != 0 {
+        fail(rc)
+    }
+    peaks.truncate(n_peaks as usize);
+    peaks
+}
+
+/// bag_peaks (mmr/mmr_accumulator.rs:379-391)
+pub fn mmr_bag_peaks(peaks: &[Digest], leaf_count: u64) -> Digest {
+    let mut out = Digest::default();
+    let rc = unsafe {
+        sys::tf21_mmr_bag_peaks(peaks.as_ptr() as *const u64, peaks.len() as u64, leaf_count,
+                                &mut out as *mut Digest as *mut u64)
+    };
+    if rc != 0 {
+        fail(rc)
+    }
+    out
 }

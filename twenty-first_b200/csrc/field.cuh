@@ -27,7 +27,7 @@ typedef uint32_t u32;
 #define TF21_PRED_MUL 1
 #endif
 #ifndef TF21_SHL_WIDE
-#define TF21_SHL_WIDE 1  /* 0: shifts on the ALU (-1.8 %), 1: two IMAD.WIDE with a 64-bit addend (best), 2: OR instead of the addend (-1.7 %); tools/ab.sh on the 2^20 batch */
+#define TF21_SHL_WIDE 0  /* limbs of x << t in gl_shlc, tools/ab.sh on the 2^20 batch (3.54 / 3.64 / 3.67 / 3.54 / 3.67 ms for 0..4): 0: C shifts (ptxas splits them over both pipes), 1: two IMAD.WIDE with a 64-bit addend, 2: OR instead of the addend, 3: low limb as a narrow IMAD + funnel shifts, 4: one plain mul.wide + ALU */
 #endif
 #ifndef TF21_SUB_WIDE
 #define TF21_SUB_WIDE 0  /* measured -3 %: the FMA pipe is as loaded as the ALU pipe */
@@ -520,28 +520,39 @@ __device__ __forceinline__ u64 gl_canonw(u64 x) {
 // x * 2^S mod p with a CANONICAL result; x any u64; compile-time 0 < S < 96 with S % 32 != 0
 // (every shift twiddle of a 32- or 64-point transform: S is a multiple of 3).
 // z = x << (S % 32) as three 32-bit limbs, then fold by 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32.
-template <int S>
+template <int S, int V = TF21_SHL_WIDE>
 __device__ __forceinline__ u64 gl_shlc(u64 x) {
     static_assert(S > 0 && S < 96 && (S & 31) != 0, "shift twiddle out of range");
     constexpr int q = S >> 5, t = S & 31;
     const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
-#if TF21_SHL_WIDE >= 1
-    const u32 mt = c_gl_pow2[t];
-    const u64 p0 = (u64)x0 * mt;
-    const u64 p1 = (u64)x1 * mt;
-#if TF21_SHL_WIDE == 2
-    // hi(p0) < 2^t and the low t bits of lo(p1) are zero: OR instead of a 64-bit addend (which costs two
-    // register moves to build the (hi(p0), 0) pair)
-    const u32 z0 = (u32)p0, z1 = (u32)p1 | (u32)(p0 >> 32), z2 = (u32)(p1 >> 32);
-#else
-    const u64 p1a = p1 + (p0 >> 32);
-    const u32 z0 = (u32)p0, z1 = (u32)p1a, z2 = (u32)(p1a >> 32);
-#endif
-#else
-    const u32 z0 = x0 << t;
-    const u32 z1 = __funnelshift_l(x0, x1, t);
-    const u32 z2 = x1 >> (32 - t);  // < 2^31
-#endif
+    u32 z0, z1, z2;
+    if constexpr (V == 3) {
+        // low limb on the FMA pipe (narrow IMAD, 2 cycles), the funnel shifts on the ALU pipe
+        z0 = x0 * c_gl_pow2[t];
+        z1 = __funnelshift_l(x0, x1, t);
+        z2 = x1 >> (32 - t);
+    } else if constexpr (V == 4) {
+        // one plain wide multiply (no addend, 4.2 cycles) for (z1:z2) of the high word, ALU for the rest
+        const u64 p1 = (u64)x1 * c_gl_pow2[t];
+        z0 = x0 << t;
+        z1 = (u32)p1 | (x0 >> (32 - t));
+        z2 = (u32)(p1 >> 32);
+    } else if constexpr (V == 1 || V == 2) {
+        const u32 mt = c_gl_pow2[t];
+        const u64 p0 = (u64)x0 * mt;
+        const u64 p1 = (u64)x1 * mt;
+        if constexpr (V == 2) {
+            // hi(p0) < 2^t and the low t bits of lo(p1) are zero: OR instead of a 64-bit addend
+            z0 = (u32)p0, z1 = (u32)p1 | (u32)(p0 >> 32), z2 = (u32)(p1 >> 32);
+        } else {
+            const u64 p1a = p1 + (p0 >> 32);
+            z0 = (u32)p0, z1 = (u32)p1a, z2 = (u32)(p1a >> 32);
+        }
+    } else {
+        z0 = x0 << t;
+        z1 = __funnelshift_l(x0, x1, t);
+        z2 = x1 >> (32 - t);  // < 2^31
+    }
     if constexpr (q == 0) {
         // (z1:z0) + z2 * EPS, z2 * EPS < 2^63: at most one wrap; carry and "r >= p" are exclusive
         u32 lo, hi, c;

@@ -27,6 +27,15 @@
 
 namespace tf21 {
 
+#ifndef TF21_SHL_SINGLE
+#define TF21_SHL_SINGLE 1  /* shift form of the single-pass 2^10 kernel (no staging, lighter ALU load): the wide-multiply form is 4 % faster there */
+#endif
+#ifndef TF21_SHL_COL
+#define TF21_SHL_COL TF21_SHL_WIDE
+#endif
+#ifndef TF21_SHL_ROW
+#define TF21_SHL_ROW TF21_SHL_WIDE
+#endif
 #ifndef TF21_FAST_COLS
 #define TF21_FAST_COLS 8
 #endif
@@ -57,13 +66,13 @@ __host__ __device__ constexpr u32 brev_bits(u32 k, int bits) {
 // register index and every shift amount is a compile-time constant by construction, so the value
 // array can never fall back to local memory (a `#pragma unroll` loop nest around inline asm with
 // labels was left partially rolled by the compiler for some sizes).
-template <bool INV, int A, int LS, int IDX>
+template <bool INV, int A, int LS, int IDX, int SHLV>
 __device__ __forceinline__ void dft_pow2_step(u64 (&v)[1 << A]) {
     constexpr int N = 1 << A;
     if constexpr (LS > A) {
         return;
     } else if constexpr (IDX >= N / 2) {
-        dft_pow2_step<INV, A, LS + 1, 0>(v);
+        dft_pow2_step<INV, A, LS + 1, 0, SHLV>(v);
     } else {
         constexpr int EU = (39 << (6 - A)) % 192;
         constexpr int m = 1 << LS, half = m >> 1;
@@ -75,7 +84,7 @@ __device__ __forceinline__ void dft_pow2_step(u64 (&v)[1 << A]) {
         constexpr int S = neg ? E - 96 : E;
         u64 t;
         if constexpr (S == 0) t = gl_canonw(v[ib]);
-        else t = gl_shlc<S>(v[ib]);
+        else t = gl_shlc<S, SHLV>(v[ib]);
         const u64 u = v[iu];
         if constexpr (!neg) {
             v[iu] = gl_addl(u, t);
@@ -84,18 +93,18 @@ __device__ __forceinline__ void dft_pow2_step(u64 (&v)[1 << A]) {
             v[iu] = gl_subl(u, t);
             v[ib] = gl_addl(u, t);
         }
-        dft_pow2_step<INV, A, LS, IDX + 1>(v);
+        dft_pow2_step<INV, A, LS, IDX + 1, SHLV>(v);
     }
 }
 
-template <bool INV, int A>
+template <bool INV, int A, int SHLV = TF21_SHL_WIDE>
 __device__ __forceinline__ void dft_pow2(u64 (&v)[1 << A]) {
-    dft_pow2_step<INV, A, 1, 0>(v);
+    dft_pow2_step<INV, A, 1, 0, SHLV>(v);
 }
 
-template <bool INV>
+template <bool INV, int SHLV = TF21_SHL_WIDE>
 __device__ __forceinline__ void dft32(u64 (&v)[32]) {
-    dft_pow2<INV, 5>(v);
+    dft_pow2<INV, 5, SHLV>(v);
 }
 
 // lazy twiddle from split tables (any u64 representative)
@@ -108,19 +117,24 @@ __device__ __forceinline__ u64 scale_factor_l(const ScaleTab &t, u64 idx) {
 // out: slice[i] = X[i] * (tw1 ? tw1[32 (i >> 5)] : 1), i = lane + 32 k2   (any u64)
 // slice: this warp's kFastS-word shared-memory slice; tw0 = t1 + lane with t1[k1*32+b] = w1024^(k1 b);
 // tw1: per-lane pointer into the inter-pass twiddle row (or nullptr).
-template <bool INV, bool MASKMUL = false>
+template <bool INV, bool MASKMUL = false, int SHLV = TF21_SHL_WIDE>
 __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64 *tw0, const u64 *tw1, u32 lane) {
 #pragma unroll 1
     for (int it = 0; it < 2; it++) {
-        dft32<INV>(v);
+        dft32<INV, SHLV>(v);
         const u64 *tw = it ? tw1 : tw0;
         u64 *out = slice + lane;
         const u32 ss = it ? 32u : 33u;
         __syncwarp();
         if (tw) {
 #pragma unroll
-            for (int k = 0; k < 32; k++)
+            for (int k = 0; k < 32; k++) {
+                if (k == 0 && it == 0) {  // t1[0][b] = omega_1024^0 = 1
+                    out[0] = v[0];
+                    continue;
+                }
                 out[k * ss] = MASKMUL ? gl_mul_mask(v[brev5(k)], __ldg(tw + 32 * k)) : gl_mul(v[brev5(k)], __ldg(tw + 32 * k));
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < 32; k++) out[k * ss] = v[brev5(k)];
@@ -188,7 +202,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
     for (int aa = 0; aa < 32; aa++) v[aa] = slice[32 * aa + lane];
     const u64 jrest = (q0 + warp) / a.w;
     // inter-pass twiddle omega_B^(i * j_rest), i = lane + 32 k2: straight from the full table when there is one
-    dft1024_warp<INV, true>(v, slice, a.t1 + lane, a.tw_full ? a.tw_full + jrest * 1024 + lane : nullptr, lane);
+    dft1024_warp<INV, true, TF21_SHL_COL>(v, slice, a.t1 + lane, a.tw_full ? a.tw_full + jrest * 1024 + lane : nullptr, lane);
     if (!a.tw_full) {
         const u64 bmask = (1ull << a.log_b) - 1;
 #pragma unroll 4
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kern
         u64 v[32];
 #pragma unroll
         for (int aa = 0; aa < 32; aa++) v[aa] = row[(u64)(32 * aa + lane) * W];
-        dft1024_warp<INV>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane);
+        dft1024_warp<INV, false, TF21_SHL_ROW>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane);
     }
     __syncthreads();
 
@@ -461,7 +475,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_single_k
         v[aa] = x;
     }
     u64 *slice = tile + warp * kFastS;
-    dft1024_warp<INV>(v, slice, a.t1 + lane, nullptr, lane);
+    dft1024_warp<INV, false, TF21_SHL_SINGLE>(v, slice, a.t1 + lane, nullptr, lane);
     u64 *out = a.dst + arr * a.dst_array_words;
 #pragma unroll 8
     for (int k2 = 0; k2 < 32; k2++) {
