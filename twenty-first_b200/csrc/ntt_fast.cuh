@@ -233,7 +233,8 @@ struct FastRowArgs {
     u64 array_words;      // n * w
     u32 w;
     u32 n1, n2, n3;       // sizes of the leading digits i_1, i_2, i_3 (1 when absent); rows = n1 n2 n3
-    u32 n_tiles;          // rows * w / 8
+    u64 n_cols_total;     // batch * rows * w word-columns over the whole batch
+    u32 n_tiles;          // rows * w / 8 when that is exact (a CTA never straddles arrays), else 0
     const u64 *t1;
     u64 post_scalar;      // 0 => none
     ScaleTab post;
@@ -249,29 +250,44 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kern
     extern __shared__ u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 tile_id = blockIdx.x % a.n_tiles;
-    const u32 b = blockIdx.x / a.n_tiles;
-    const u32 tc0 = tile_id * kFastCols;
     const u32 rows = a.n1 * a.n2 * a.n3;
+    const u32 rw = rows * W;  // word-columns per array
+    // word-column g of the whole batch: array b = g / rw, column tc = g % rw.  A CTA takes 8 consecutive g
+    // (for rows * W < 8, i.e. n = 2^11 / 2^12, they span several arrays of the batch).
+    const u64 g0 = (u64)blockIdx.x * kFastCols;
+    // rows * W a multiple of 8 (every n >= 2^13): a CTA stays inside one array -- one 32-bit division per CTA
+    u64 b_cta = 0;
+    u32 tc_cta = 0;
+    if (a.n_tiles) {
+        b_cta = blockIdx.x / a.n_tiles;
+        tc_cta = (blockIdx.x - (u32)b_cta * a.n_tiles) * kFastCols;
+    }
     {
-        const u32 tc = tc0 + warp;
-        const u32 op = tc / W, c = tc - op * W;
-        const u32 i1 = op % a.n1, r23 = op / a.n1;
-        const u32 i2 = r23 % a.n2, i3 = r23 / a.n2;
-        const u64 rho = ((u64)i1 * a.n2 + i2) * a.n3 + i3;
-        const u64 *row = a.src + (u64)b * a.array_words + rho * 1024 * W + c;
-        u64 v[32];
+        const u64 g = g0 + warp;
+        if (g < a.n_cols_total) {
+            const u64 b = a.n_tiles ? b_cta : g / rw;
+            const u32 tc = a.n_tiles ? tc_cta + warp : (u32)(g - b * rw);
+            const u32 op = tc / W, c = tc - op * W;
+            const u32 i1 = op % a.n1, r23 = op / a.n1;
+            const u32 i2 = r23 % a.n2, i3 = r23 / a.n2;
+            const u64 rho = ((u64)i1 * a.n2 + i2) * a.n3 + i3;
+            const u64 *row = a.src + b * a.array_words + rho * 1024 * W + c;
+            u64 v[32];
 #pragma unroll
-        for (int aa = 0; aa < 32; aa++) v[aa] = row[(u64)(32 * aa + lane) * W];
-        dft1024_warp<INV, false, TF21_SHL_ROW>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane);
+            for (int aa = 0; aa < 32; aa++) v[aa] = row[(u64)(32 * aa + lane) * W];
+            dft1024_warp<INV, false, TF21_SHL_ROW>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane);
+        }
     }
     __syncthreads();
 
     // stage out: word (i_k = r, tc) -> dst[r * rows * w + tc]
     {
         const u32 c8 = lane % kFastCols, rsub = lane / kFastCols;
-        const u32 tc = tc0 + c8;
-        u64 *dst = a.dst + (u64)b * a.array_words + tc;
+        const u64 g = g0 + c8;
+        if (g >= a.n_cols_total) return;
+        const u64 b = a.n_tiles ? b_cta : g / rw;
+        const u32 tc = a.n_tiles ? tc_cta + c8 : (u32)(g - b * rw);
+        u64 *dst = a.dst + b * a.array_words + tc;
         const u64 *tl = tile + c8 * kFastS;
         const u64 ostride = (u64)rows * W;
         const u64 op = tc / W;  // element index = op + rows * r
@@ -454,35 +470,38 @@ struct FastSingleArgs {
     ScaleTab pre, post;
 };
 
-// n = 1024, w = 1: one warp per array of the batch, no global staging at all.
-template <bool INV>
+// n = 1024: one warp per word-column (array, c) of the batch, no global staging at all.  For w = 3 the three
+// warps of an array interleave their 8-byte accesses (stride 24 B): every sector is still used completely.
+template <bool INV, u32 W>
 __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_single_kernel(const FastSingleArgs a) {
     extern __shared__ u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u64 arr = (u64)blockIdx.x * kFastCols + warp;
-    if (arr >= a.batch) return;
-    const u64 *row = a.src + arr * a.src_array_words;
+    const u64 g = (u64)blockIdx.x * kFastCols + warp;
+    if (g >= a.batch * W) return;
+    const u64 arr = g / W;
+    const u32 c = (u32)(g - arr * W);
+    const u64 *row = a.src + arr * a.src_array_words + c;
     u64 v[32];
 #pragma unroll
     for (int aa = 0; aa < 32; aa++) {
         const u64 j = 32 * aa + lane;
         u64 x = 0;
         if (j < a.n_in_elems) {
-            x = row[j];
+            x = row[j * W];
             if (a.pre.lo) x = gl_mul(x, scale_factor(a.pre, j));
         }
         v[aa] = x;
     }
     u64 *slice = tile + warp * kFastS;
     dft1024_warp<INV, false, TF21_SHL_SINGLE>(v, slice, a.t1 + lane, nullptr, lane);
-    u64 *out = a.dst + arr * a.dst_array_words;
+    u64 *out = a.dst + arr * a.dst_array_words + c;
 #pragma unroll 8
     for (int k2 = 0; k2 < 32; k2++) {
         u64 x = slice[lane + 32 * k2];
         if (a.post_scalar) x = gl_mul(x, a.post_scalar);
         if (a.post.lo) x = gl_mul(x, scale_factor(a.post, (u64)(lane + 32 * k2)));
-        out[lane + 32 * k2] = gl_canonw(x);
+        out[(u64)(lane + 32 * k2) * W] = gl_canonw(x);
     }
 }
 
@@ -756,7 +775,7 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
                    int inverse, ScaleTab pre, ScaleTab post, u64 post_scalar, u64 *scratch, cudaStream_t st) {
     const u32 log_n = ilog2_u64(n);
     const u64 array_words = n * w;
-    if (log_n < 10 || (log_n == 10 && w != 1) || log_n == 11 || log_n == 12)
+    if (log_n < 10)
         return ntt_run_generic(tabs, src, n_in, dst, n, w, batch, inverse, pre, post, post_scalar, scratch, st);
 
     const u64 *t1 = nullptr;
@@ -776,10 +795,14 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         a.post_scalar = post_scalar;
         a.pre = pre;
         a.post = post;
-        u64 grid = (batch + kFastCols - 1) / kFastCols;
+        u64 grid = (batch * w + kFastCols - 1) / kFastCols;
         if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-        if (inverse) return launch_fast(ntt1024_single_kernel<true>, (unsigned)grid, a, st);
-        return launch_fast(ntt1024_single_kernel<false>, (unsigned)grid, a, st);
+        if (w == 1) {
+            if (inverse) return launch_fast_named("ntt1024_single_kernel", ntt1024_single_kernel<true, 1>, (unsigned)grid, a, st);
+            return launch_fast_named("ntt1024_single_kernel", ntt1024_single_kernel<false, 1>, (unsigned)grid, a, st);
+        }
+        if (inverse) return launch_fast_named("ntt1024_single_kernel", ntt1024_single_kernel<true, 3>, (unsigned)grid, a, st);
+        return launch_fast_named("ntt1024_single_kernel", ntt1024_single_kernel<false, 3>, (unsigned)grid, a, st);
     }
 
     // ---- plan: logs of the leading (column) passes, the last pass is always the 1024-point row pass ----
@@ -904,11 +927,12 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     a.n2 = n_lead > 1 ? 1u << lead[1] : 1u;
     a.n3 = n_lead > 2 ? 1u << lead[2] : 1u;
     const u64 rows = n >> 10;
-    a.n_tiles = (u32)(rows * w / kFastCols);
+    a.n_cols_total = batch * rows * w;
+    a.n_tiles = (rows * w) % kFastCols == 0 ? (u32)(rows * w / kFastCols) : 0u;
     a.t1 = t1;
     a.post_scalar = post_scalar;
     a.post = post;
-    u64 grid = batch * a.n_tiles;
+    u64 grid = (a.n_cols_total + kFastCols - 1) / kFastCols;
     if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
     if (w == 1) {
         if (inverse) return launch_fast_named("ntt1024_row_kernel", ntt1024_row_kernel<true, 1>, (unsigned)grid, a, st);

@@ -53,8 +53,10 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         t.constants_ready = true;
     }
     *out = &t;
