@@ -54,6 +54,17 @@ extern "C" {
     pub fn tf21_poly_mul_dev(a: *const u64, n_a: u64, b: *const u64, n_b: u64, width: u32, out: *mut u64,
                              s: tf21_stream_t) -> c_int;
 
+    pub fn tf21_poly_evaluate_batch_dev(polys: *const u64, n: u64, n_polys: u64, width: u32, points: *const u64,
+                                        n_points: u64, out: *mut u64, s: tf21_stream_t) -> c_int;
+    pub fn tf21_batch_coset_extrapolate(offset_raw: u64, codeword_length: u64, codewords: *const u64, n_codewords: u64,
+                                        width: u32, points: *const u64, n_points: u64, out: *mut u64) -> c_int;
+    pub fn tf21_batch_coset_extrapolate_dev(offset_raw: u64, codeword_length: u64, codewords: *const u64,
+                                            n_codewords: u64, width: u32, points: *const u64, n_points: u64,
+                                            out: *mut u64, s: tf21_stream_t) -> c_int;
+    pub fn tf21_tip5_sample_indices(state: *mut u64, upper_bound: u32, num_indices: u64, out: *mut u32) -> c_int;
+    pub fn tf21_poly_square(a: *const u64, n_a: u64, width: u32, out: *mut u64) -> c_int;
+    pub fn tf21_poly_square_dev(a: *const u64, n_a: u64, width: u32, out: *mut u64, s: tf21_stream_t) -> c_int;
+
     pub fn tf21_tip5_permute(states: *mut u64, count: u64) -> c_int;
     pub fn tf21_tip5_hash_10(input: *const u64, count: u64, out: *mut u64) -> c_int;
     pub fn tf21_tip5_hash_pairs(pairs: *const u64, count: u64, out: *mut u64) -> c_int;

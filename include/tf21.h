@@ -118,7 +118,32 @@ int tf21_poly_mul(const uint64_t *a, uint64_t n_a, const uint64_t *b, uint64_t n
 int tf21_poly_mul_dev(const uint64_t *d_a, uint64_t n_a, const uint64_t *d_b, uint64_t n_b, uint32_t width,
                       uint64_t *d_out, tf21_stream_t stream);
 
+/* Polynomial::fast_square (polynomial.rs:780-802): out[0 .. 2 n_a - 1) = a * a with one forward transform
+ * (tf21_poly_mul_dev does the same when both operands are the same buffer).                          */
+int tf21_poly_square(const uint64_t *a, uint64_t n_a, uint32_t width, uint64_t *out);
+int tf21_poly_square_dev(const uint64_t *d_a, uint64_t n_a, uint32_t width, uint64_t *d_out,
+                         tf21_stream_t stream);
+
+/* Polynomial::evaluate (polynomial.rs:309-319) of n_polys device-resident polynomials of n coefficients each
+ * in n_points points (host array, same width as the coefficients): out[(poly * n_points + point) * width ..].  */
+int tf21_poly_evaluate_batch_dev(const uint64_t *d_polys, uint64_t n, uint64_t n_polys, uint32_t width,
+                                 const uint64_t *points, uint64_t n_points, uint64_t *d_out,
+                                 tf21_stream_t stream);
+/* Polynomial::{batch_,par_batch_}coset_extrapolate (polynomial.rs:2117-2331): n_codewords codewords of
+ * codeword_length (a power of two) values on the coset offset * <omega>, extrapolated to n_points points;
+ * out[(codeword * n_points + point) * width ..] like the reference's flat_map.                          */
+int tf21_batch_coset_extrapolate(uint64_t offset_raw, uint64_t codeword_length, const uint64_t *codewords,
+                                 uint64_t n_codewords, uint32_t width, const uint64_t *points,
+                                 uint64_t n_points, uint64_t *out);
+int tf21_batch_coset_extrapolate_dev(uint64_t offset_raw, uint64_t codeword_length,
+                                     const uint64_t *d_codewords, uint64_t n_codewords, uint32_t width,
+                                     const uint64_t *points, uint64_t n_points, uint64_t *d_out,
+                                     tf21_stream_t stream);
+
 /* ---- Tip5 (tip5/mod.rs:529-533, 559-586, 617-623; sponge.rs:41-56) -------------------------- */
+/* Tip5::sample_indices (tip5/mod.rs:636-656): `state` = the sponge's 16 raw words, updated in place;
+ * upper_bound must be a power of two (TF21_E_LEN_NOT_POW2 <-> the reference's assert).                  */
+int tf21_tip5_sample_indices(uint64_t *state, uint32_t upper_bound, uint64_t num_indices, uint32_t *out);
 int tf21_tip5_permute(uint64_t *states /*16 words each*/, uint64_t count);
 int tf21_tip5_hash_10(const uint64_t *in /*10 words each*/, uint64_t count, uint64_t *out /*5 each*/);
 int tf21_tip5_hash_pairs(const uint64_t *pairs /*left(5)|right(5)*/, uint64_t count, uint64_t *out);

@@ -100,6 +100,11 @@ class Oracle:
         L.oracle_merkle_par_new.argtypes = [_u64p, u64, _u64p, i32, u64]
         L.oracle_merkle_sequential_frugal_root.argtypes = [_u64p, u64, _u64p]
         L.oracle_merkle_par_frugal_root.argtypes = [_u64p, u64, _u64p, i32, u64]
+        L.oracle_poly_evaluate_w.argtypes = [_u64p, u64, u32, _u64p, _u64p]
+        L.oracle_poly_evaluate_w.restype = None
+        L.oracle_batch_coset_extrapolate.argtypes = [u64, u64, _u64p, u64, u32, _u64p, u64, _u64p]
+        L.oracle_tip5_sample_indices.argtypes = [_u64p, u32, u64, ctypes.POINTER(ctypes.c_uint32)]
+        L.oracle_tip5_sample_indices.restype = None
         L.oracle_mmr_peaks_from_leafs.argtypes = [_u64p, u64, _u64p]
         L.oracle_mmr_peaks_from_leafs.restype = u64
         L.oracle_mmr_bag_peaks.argtypes = [_u64p, u64, u64, _u64p]
@@ -265,6 +270,27 @@ class Oracle:
         root = np.zeros(5, dtype=np.uint64)
         rc = self.lib.oracle_merkle_par_frugal_root(_ptr(leafs if n else root), n, _ptr(root), threads, cutoff)
         return rc, root
+
+    def poly_evaluate_w(self, coeffs: np.ndarray, width: int, x: np.ndarray) -> np.ndarray:
+        out = np.zeros(width, dtype=np.uint64)
+        buf = coeffs if coeffs.size else np.zeros(width, dtype=np.uint64)
+        self.lib.oracle_poly_evaluate_w(_ptr(buf), coeffs.size // width, width, _ptr(np.ascontiguousarray(x)), _ptr(out))
+        return out
+
+    def batch_coset_extrapolate(self, offset_raw: int, n: int, codewords: np.ndarray, width: int, points: np.ndarray):
+        n_cw = codewords.size // (n * width)
+        n_pts = points.size // width
+        out = np.zeros(max(1, n_cw * n_pts * width), dtype=np.uint64)
+        rc = self.lib.oracle_batch_coset_extrapolate(offset_raw, n, _ptr(codewords), n_cw, width, _ptr(points), n_pts,
+                                                     _ptr(out))
+        return rc, out[: n_cw * n_pts * width]
+
+    def tip5_sample_indices(self, state: np.ndarray, upper_bound: int, num_indices: int) -> np.ndarray:
+        """state (16 raw words) is advanced in place like `&mut self`"""
+        out = np.zeros(max(1, num_indices), dtype=np.uint32)
+        self.lib.oracle_tip5_sample_indices(_ptr(state), upper_bound, num_indices,
+                                            out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+        return out[:num_indices]
 
     def mmr_peaks_from_leafs(self, leafs: np.ndarray) -> np.ndarray:
         """MmrAccumulator::peaks_from_leafs (mmr_accumulator.rs:96-115), any leaf count"""

@@ -746,3 +746,53 @@ int oracle_poly_fast_multiply(const uint64_t *a, uint64_t na, const uint64_t *b,
     free(r);
     return rc;
 }
+
+/* ---- out-of-domain evaluation / coset extrapolation (next-wave checker) ---------------
+ * Polynomial::evaluate, polynomial.rs:309-319 (Horner from the highest coefficient), for BFE (w = 1) or XFE
+ * (w = 3) coefficients and a point of the same field. */
+void oracle_poly_evaluate_w(const uint64_t *coeffs, uint64_t n_coeffs, uint32_t w, const uint64_t *x, uint64_t *out) {
+    uint64_t acc[3] = {0, 0, 0};
+    for (uint64_t i = n_coeffs; i-- > 0;) {
+        if (w == 1) {
+            acc[0] = bfe_add(bfe_mul(acc[0], x[0]), coeffs[i]);
+        } else {
+            uint64_t t[3];
+            xfe_mul(acc, x, t);
+            for (int k = 0; k < 3; k++) acc[k] = bfe_add(t[k], coeffs[3 * i + k]);
+        }
+    }
+    for (uint32_t k = 0; k < w; k++) out[k] = acc[k];
+}
+
+/* Polynomial::naive_coset_extrapolate applied per codeword (polynomial.rs:2135-2147, 2310-2331 without the
+ * modular reduction, which does not change the values): intt, scale by offset^-1, evaluate in every point.
+ * out[(codeword * n_points + point) * w ..] */
+int oracle_batch_coset_extrapolate(uint64_t offset_raw, uint64_t n, const uint64_t *codewords, uint64_t n_codewords,
+                                   uint32_t w, const uint64_t *points, uint64_t n_points, uint64_t *out) {
+    if (n == 0 || (n & (n - 1))) return ORACLE_E_LEN_NOT_POW2;
+    uint64_t *coeffs = (uint64_t *)malloc(sizeof(uint64_t) * n * w);
+    int rc = 0;
+    for (uint64_t c = 0; c < n_codewords && !rc; c++) {
+        rc = oracle_coset_interpolate(codewords + c * n * w, n, w, offset_raw, coeffs);
+        for (uint64_t p = 0; p < n_points && !rc; p++)
+            oracle_poly_evaluate_w(coeffs, n, w, points + p * w, out + (c * n_points + p) * w);
+    }
+    free(coeffs);
+    return rc;
+}
+
+/* Tip5::sample_indices, tip5/mod.rs:636-656 (squeeze = emit state[..RATE], then permute, :693-698) */
+void oracle_tip5_sample_indices(uint64_t state[16], uint32_t upper_bound, uint64_t num_indices, uint32_t *out) {
+    tip5_setup();
+    uint64_t produced = 0, buffer[10];
+    int next_in_buffer = 10;
+    while (produced < num_indices) {
+        if (next_in_buffer == 10) {
+            memcpy(buffer, state, sizeof(buffer));
+            oracle_tip5_permutation(state);
+            next_in_buffer = 0;
+        }
+        uint64_t element = buffer[next_in_buffer++];
+        if (bfe_value(element) != 0xFFFFFFFF00000000ull) out[produced++] = (uint32_t)bfe_value(element) % upper_bound;
+    }
+}

@@ -600,3 +600,70 @@ def test_mmr_bag_peaks_reference_snapshot(tf, oracle):
     for count in (0b11_1111_1111, (1 << 40) + 5, (1 << 64) - 1):
         got = tf.MmrAccumulator(peaks, count).bag_peaks()
         assert np.array_equal(got, oracle.mmr_bag_peaks(peaks, count))
+
+
+@pytest.mark.parametrize("na,width", [(1, 1), (1, 3), (2, 1), (3, 3), (33, 1), (64, 3), (1000, 1), (1025, 3), (5000, 1)])
+def test_poly_fast_square_matches_oracle(tf, oracle, na, width):
+    """Polynomial::fast_square (polynomial.rs:780-802) == fast_multiply(self, self) of the oracle"""
+    a = rnd(0xA000 + na, na * width)
+    rc, want = oracle.poly_fast_multiply(a, a.copy(), width)
+    assert rc == 0
+    got = tf.Polynomial(a.reshape(na) if width == 1 else a.reshape(na, 3)).fast_square()
+    assert np.array_equal(got.coefficients.reshape(-1), want)
+
+
+# ---- next wave (SURVEY.md 8f-2): coset extrapolation to out-of-domain points -------------------------
+@pytest.mark.parametrize("log_n,n_cw,n_pts,width", [(0, 1, 1, 1), (1, 2, 3, 3), (5, 2, 2, 1), (8, 3, 5, 3),
+                                                    (10, 7, 4, 1), (12, 2, 9, 3), (16, 3, 2, 1), (18, 2, 3, 3)])
+def test_batch_coset_extrapolate_matches_oracle(tf, oracle, log_n, n_cw, n_pts, width):
+    """polynomial.rs:2188-2331; the doc example (:2202-2213) is the first hard-coded case below"""
+    n = 1 << log_n
+    cws = rnd(0xB000 + log_n, n * width * n_cw)
+    pts = rnd(0xB100 + log_n, n_pts * width)
+    offset = tf.BFieldElement.generator()
+    rc, want = oracle.batch_coset_extrapolate(offset, n, cws, width, pts)
+    assert rc == 0
+    got = tf.Polynomial.par_batch_coset_extrapolate(offset, n, cws if width == 1 else cws.reshape(-1, 3),
+                                                    pts if width == 1 else pts.reshape(-1, 3))
+    assert np.array_equal(got.reshape(-1), want)
+
+
+def test_batch_coset_extrapolate_reference_doc_example(tf, oracle):
+    n = 1 << 5
+    cws = np.concatenate([oracle.to_raw([3] * n), oracle.to_raw([2] * n)])
+    pts = oracle.to_raw([0, 1])
+    got = tf.Polynomial.batch_coset_extrapolate(tf.BFieldElement.new(7), n, cws, pts)
+    assert oracle.to_values(got).tolist() == [3, 3, 2, 2]
+    with pytest.raises(tf.Tf21Error):
+        tf.Polynomial.batch_coset_extrapolate(tf.BFieldElement.new(7), 12, cws[:24], pts)
+
+
+def test_extrapolation_in_the_domain_reproduces_the_codeword(tf, oracle):
+    """size-independent property: extrapolating to points of the coset itself returns the codeword values"""
+    log_n, width = 14, 3
+    n = 1 << log_n
+    cw = rnd(0xB200, n * width)
+    offset = tf.BFieldElement.generator()
+    omega = oracle.primitive_root_of_unity(n)
+    idx = [0, 1, 2, 77, n // 2, n - 1]
+    pts = np.zeros((len(idx), 3), dtype=np.uint64)
+    for k, i in enumerate(idx):
+        pts[k, 0] = oracle.bfe_mul(offset, oracle.bfe_mod_pow(omega, i))
+    got = tf.Polynomial.coset_extrapolate(offset, cw.reshape(n, 3), pts)
+    assert np.array_equal(got, cw.reshape(n, 3)[idx])
+
+
+def test_tip5_sample_indices_matches_oracle(tf, oracle):
+    """tip5/mod.rs:636-656, incl. a state that squeezes BFieldElement::MAX (dropped by the rejection sampling)"""
+    for seed, ub, count in [(1, 1 << 10, 1), (2, 1 << 20, 45), (3, 1, 12), (4, 1 << 31, 333), (5, 1 << 16, 10)]:
+        state = rnd(0xC000 + seed, 16)
+        if seed == 5:
+            state[3] = np.uint64(oracle.bfe_new(0xFFFFFFFF00000000))  # MAX in the first squeeze
+        want_state = state.copy()
+        want = oracle.tip5_sample_indices(want_state, ub, count)
+        got_state = state.copy()
+        got = tf.Tip5.sample_indices(got_state, ub, count)
+        assert np.array_equal(got, want)
+        assert np.array_equal(got_state, want_state)
+    with pytest.raises(tf.Tf21Error):
+        tf.Tip5.sample_indices(rnd(1, 16), 12, 3)

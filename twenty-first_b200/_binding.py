@@ -53,6 +53,12 @@ SIGNATURES = {
     "tf21_coset_lde_dev": (i32, [vp, u64, u64, u64, u64, u32, vp, vp]),
     "tf21_poly_mul": (i32, [vp, u64, vp, u64, u32, vp]),
     "tf21_poly_mul_dev": (i32, [vp, u64, vp, u64, u32, vp, vp]),
+    "tf21_poly_evaluate_batch_dev": (i32, [vp, u64, u64, u32, vp, u64, vp, vp]),
+    "tf21_batch_coset_extrapolate": (i32, [u64, u64, vp, u64, u32, vp, u64, vp]),
+    "tf21_batch_coset_extrapolate_dev": (i32, [u64, u64, vp, u64, u32, vp, u64, vp, vp]),
+    "tf21_tip5_sample_indices": (i32, [vp, u32, u64, vp]),
+    "tf21_poly_square": (i32, [vp, u64, u32, vp]),
+    "tf21_poly_square_dev": (i32, [vp, u64, u32, vp, vp]),
     "tf21_tip5_permute": (i32, [vp, u64]),
     "tf21_tip5_hash_10": (i32, [vp, u64, vp]),
     "tf21_tip5_hash_pairs": (i32, [vp, u64, vp]),

@@ -110,6 +110,37 @@ class Polynomial:
                                     _ptr(out)))
         return Polynomial(out)
 
+    def fast_square(self) -> "Polynomial":
+        """polynomial.rs:780-802; trailing zero coefficients are kept"""
+        na = self.coefficients.shape[0]
+        n = 2 * na - 1 if na else 0
+        out = np.zeros((n,) if self.width == 1 else (n, 3), dtype=np.uint64)
+        B.check(B.lib.tf21_poly_square(_ptr(self.coefficients), na, self.width, _ptr(out)))
+        return Polynomial(out)
+
+    @staticmethod
+    def par_batch_coset_extrapolate(domain_offset_raw: int, codeword_length: int, codewords: np.ndarray,
+                                    points: np.ndarray) -> np.ndarray:
+        """polynomial.rs:2188-2331 (batch_ / par_batch_coset_extrapolate): codewords and points of the same field;
+        result[(codeword, point)] flattened like the reference's flat_map.  Panics (raises) if the codeword
+        length is not a power of two."""
+        codewords = _words(np.ascontiguousarray(codewords))
+        points = _words(np.ascontiguousarray(points))
+        w = 3 if (codewords.ndim == 2 and codewords.shape[1] == 3) else 1
+        n_cw = codewords.size // (codeword_length * w) if codeword_length else 0
+        n_pts = points.size // w
+        out = np.zeros((n_cw * n_pts,) if w == 1 else (n_cw * n_pts, 3), dtype=np.uint64)
+        B.check(B.lib.tf21_batch_coset_extrapolate(domain_offset_raw, codeword_length, _ptr(codewords), n_cw, w,
+                                                   _ptr(points), n_pts, _ptr(out)))
+        return out
+
+    batch_coset_extrapolate = par_batch_coset_extrapolate
+
+    @staticmethod
+    def coset_extrapolate(domain_offset_raw: int, codeword: np.ndarray, points: np.ndarray) -> np.ndarray:
+        """polynomial.rs:2117-2127"""
+        return Polynomial.par_batch_coset_extrapolate(domain_offset_raw, codeword.shape[0], codeword, points)
+
     @staticmethod
     def fast_coset_interpolate(offset_raw: int, values: np.ndarray) -> "Polynomial":
         """polynomial.rs:1907-1918"""
@@ -169,6 +200,16 @@ class Tip5:
         inp = _words(np.ascontiguousarray(inp))
         out = np.zeros(5, dtype=np.uint64)
         B.check(B.lib.tf21_tip5_hash_varlen(_ptr(inp), inp.size, _ptr(out)))
+        return out
+
+    @staticmethod
+    def sample_indices(state: np.ndarray, upper_bound: int, num_indices: int) -> np.ndarray:
+        """tip5/mod.rs:636-656 on the sponge state `state` (16 raw words, advanced in place like `&mut self`);
+        panics (raises) unless upper_bound is a power of two"""
+        _words(state)
+        out = np.zeros(num_indices, dtype=np.uint32)
+        B.check(B.lib.tf21_tip5_sample_indices(_ptr(state), upper_bound, num_indices,
+                                               out.ctypes.data if num_indices else None))
         return out
 
     @staticmethod

@@ -210,7 +210,9 @@ __global__ void ntt_row_pass_kernel(const RowPassArgs a) {
 // BFieldElement product; every term of the XFieldElement product (x_field_element.rs:512-535) is a
 // product of exactly two words, so the whole result is the plain mod-p product times `rinv` = 2^-64.
 // Output words are lazy (any u64): the inverse transform that follows accepts any representative.
-__global__ void hadamard_kernel(u64 *__restrict__ a, const u64 *__restrict__ b, u64 n_elems, u32 w, u64 rinv) {
+// (a and b may be the same buffer: Polynomial::fast_square, polynomial.rs:780-802; every thread reads its
+// element of both operands before it writes)
+__global__ void hadamard_kernel(u64 *a, const u64 *b, u64 n_elems, u32 w, u64 rinv) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_elems) return;
     if (w == 1) {
@@ -226,6 +228,93 @@ __global__ void hadamard_kernel(u64 *__restrict__ a, const u64 *__restrict__ b, 
     a[3 * i] = gl_mul(r0, rinv);
     a[3 * i + 1] = gl_mul(r1, rinv);
     a[3 * i + 2] = gl_mul(r2, rinv);
+}
+
+// ---- out-of-domain evaluation (next wave) --------------------------------------------
+// Polynomial::evaluate (Horner, polynomial.rs:309-319) for many (polynomial, point) pairs: the tail of
+// par_batch_coset_extrapolate (polynomial.rs:2255-2331).  Coefficients and accumulators are raw Montgomery
+// words; the point is passed as its canonical *values* x' = raw * 2^-64, so that the plain mod-p product
+// acc * x' is the raw word of acc * x (for XFieldElements term by term, x_field_element.rs:512-535).
+template <u32 W>
+struct EvalElem {
+    u64 c[W];
+};
+template <u32 W>
+__device__ __forceinline__ EvalElem<W> eval_mul(const EvalElem<W> &l, const EvalElem<W> &r) {
+    EvalElem<W> o;
+    if constexpr (W == 1) {
+        o.c[0] = gl_mulc(l.c[0], r.c[0]);
+    } else {
+        const u64 c = l.c[0], b = l.c[1], a = l.c[2], f = r.c[0], e = r.c[1], d = r.c[2];
+        const u64 ae = gl_mulc(a, e), bd = gl_mulc(b, d), ad = gl_mulc(a, d);
+        o.c[0] = gl_sub(gl_sub(gl_mulc(c, f), ae), bd);
+        o.c[1] = gl_add(gl_add(gl_sub(gl_add(gl_mulc(b, f), gl_mulc(c, e)), ad), ae), bd);
+        o.c[2] = gl_add(gl_add(gl_add(gl_mulc(a, f), gl_mulc(b, e)), gl_mulc(c, d)), ad);
+    }
+    return o;
+}
+template <u32 W>
+__device__ __forceinline__ EvalElem<W> eval_add(const EvalElem<W> &l, const EvalElem<W> &r) {
+    EvalElem<W> o;
+#pragma unroll
+    for (u32 k = 0; k < W; k++) o.c[k] = gl_add(l.c[k], r.c[k]);
+    return o;
+}
+
+constexpr u32 kEvalThreads = 256;
+// grid = (n_points, n_polys).  polys: n_polys arrays of n elements (canonical raw words); points_val: canonical
+// values of the points; out[(poly * n_points + point) * W ..]: raw words, canonical.
+template <u32 W>
+__global__ void __launch_bounds__(kEvalThreads) poly_eval_kernel(const u64 *__restrict__ polys, u64 n,
+                                                                  const u64 *__restrict__ points_val, u32 n_points,
+                                                                  u64 *__restrict__ out) {
+    __shared__ u64 sh[kEvalThreads * W];
+    const u32 tid = threadIdx.x;
+    const u32 point = blockIdx.x;
+    const u64 poly = blockIdx.y;
+    const u64 *coeffs = polys + poly * n * W;
+    EvalElem<W> x;
+#pragma unroll
+    for (u32 k = 0; k < W; k++) x.c[k] = points_val[point * W + k];
+    // thread t owns coefficients [t * chunk, (t + 1) * chunk): Horner from the top of its chunk
+    const u64 chunk = (n + kEvalThreads - 1) / kEvalThreads;
+    const u64 lo = (u64)tid * chunk;
+    const u64 hi = lo + chunk < n ? lo + chunk : n;
+    EvalElem<W> acc;
+#pragma unroll
+    for (u32 k = 0; k < W; k++) acc.c[k] = 0;
+    for (u64 i = hi; i > lo; i--) {
+        EvalElem<W> ci;
+#pragma unroll
+        for (u32 k = 0; k < W; k++) ci.c[k] = coeffs[(i - 1) * W + k];
+        acc = eval_add<W>(eval_mul<W>(acc, x), ci);
+    }
+    // y = x^chunk (values, so products of values stay values)
+    EvalElem<W> y, base = x;
+#pragma unroll
+    for (u32 k = 0; k < W; k++) y.c[k] = k == 0 ? 1ull : 0ull;
+    for (u64 e = chunk; e; e >>= 1) {
+        if (e & 1) y = eval_mul<W>(y, base);
+        base = eval_mul<W>(base, base);
+    }
+    // tree: P_t <- P_t + P_(t + s) * y^s, s = 1, 2, 4, ..
+    for (u32 s = 1; s < kEvalThreads; s <<= 1) {
+#pragma unroll
+        for (u32 k = 0; k < W; k++) sh[tid * W + k] = acc.c[k];
+        __syncthreads();
+        if ((tid & (2 * s - 1)) == 0) {
+            EvalElem<W> other;
+#pragma unroll
+            for (u32 k = 0; k < W; k++) other.c[k] = sh[(tid + s) * W + k];
+            acc = eval_add<W>(acc, eval_mul<W>(other, y));
+        }
+        y = eval_mul<W>(y, y);
+        __syncthreads();
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (u32 k = 0; k < W; k++) out[(poly * n_points + point) * W + k] = acc.c[k];
+    }
 }
 
 // ---- host planning ------------------------------------------------------------------------------

@@ -454,14 +454,15 @@ int tf21_poly_mul_dev(const uint64_t *d_a, uint64_t n_a, const uint64_t *d_b, ui
     DeviceTables *t;
     TF21_TRY(get_tables(&t));
     cudaStream_t st = (cudaStream_t)stream;
+    const bool square = d_a == d_b && n_a == n_b;  // fast_square (polynomial.rs:780-802): one forward transform
     Scratch l(st), r(st);
     TF21_TRY(l.alloc(order * width));
-    TF21_TRY(r.alloc(order * width));
+    if (!square || order != len) TF21_TRY(r.alloc(order * width));
     // resize(order, ZERO) + ntt, fused: the transforms read only the n_a / n_b coefficients that exist
     TF21_TRY(ntt_run_locked(*t, d_a, n_a, l.p, order, width, 1, 0, NO_SCALE, NO_SCALE, 0, st));
-    TF21_TRY(ntt_run_locked(*t, d_b, n_b, r.p, order, width, 1, 0, NO_SCALE, NO_SCALE, 0, st));
+    if (!square) TF21_TRY(ntt_run_locked(*t, d_b, n_b, r.p, order, width, 1, 0, NO_SCALE, NO_SCALE, 0, st));
     const u64 rinv = hgl_inv(GL_EPS);  // 2^-64 mod p
-    TF21_LAUNCH(hadamard_kernel, grid_for(order, 256), 256, 0, st, l.p, r.p, order, width, rinv);
+    TF21_LAUNCH(hadamard_kernel, grid_for(order, 256), 256, 0, st, l.p, square ? l.p : r.p, order, width, rinv);
     const u64 post_scalar = hgl_inv(order % GL_P);
     if (order == len) {
         TF21_TRY(ntt_run_locked(*t, l.p, order, d_out, order, width, 1, 1, NO_SCALE, NO_SCALE,
@@ -473,6 +474,24 @@ int tf21_poly_mul_dev(const uint64_t *d_a, uint64_t n_a, const uint64_t *d_b, ui
         TF21_TRY(ntt_run_locked(*t, l.p, order, r.p, order, width, 1, 1, NO_SCALE, NO_SCALE, post_scalar, st));
         TF21_CUDA(cudaMemcpyAsync(d_out, r.p, len * width * sizeof(u64), cudaMemcpyDeviceToDevice, st));  // truncate
     }
+    return 0;
+}
+
+int tf21_poly_square_dev(const uint64_t *d_a, uint64_t n_a, uint32_t width, uint64_t *d_out, tf21_stream_t stream) {
+    return tf21_poly_mul_dev(d_a, n_a, d_a, n_a, width, d_out, stream);
+}
+
+int tf21_poly_square(const uint64_t *a, uint64_t n_a, uint32_t width, uint64_t *out) {
+    if (width != 1 && width != 3) return TF21_E_BAD_ARG;
+    if (n_a == 0) return 0;
+    if (!a || !out) return TF21_E_BAD_ARG;
+    const u64 len = 2 * n_a - 1;
+    DevBuf da, dout;
+    TF21_TRY(da.alloc(n_a * width));
+    TF21_TRY(dout.alloc(len * width));
+    TF21_CUDA(cudaMemcpy(da.p, a, n_a * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_poly_square_dev(da.p, n_a, width, dout.p, nullptr));
+    TF21_CUDA(cudaMemcpy(out, dout.p, len * width * sizeof(u64), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -489,6 +508,80 @@ int tf21_poly_mul(const uint64_t *a, uint64_t n_a, const uint64_t *b, uint64_t n
     TF21_CUDA(cudaMemcpy(db.p, b, n_b * width * sizeof(u64), cudaMemcpyHostToDevice));
     TF21_TRY(tf21_poly_mul_dev(da.p, n_a, db.p, n_b, width, dout.p, nullptr));
     TF21_CUDA(cudaMemcpy(out, dout.p, len * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- out-of-domain evaluation / coset extrapolation (next wave) ---------------------------
+int tf21_poly_evaluate_batch_dev(const uint64_t *d_polys, uint64_t n, uint64_t n_polys, uint32_t width,
+                                 const uint64_t *points, uint64_t n_points, uint64_t *d_out, tf21_stream_t stream) {
+    if (width != 1 && width != 3) return TF21_E_BAD_ARG;
+    if (n_polys == 0 || n_points == 0) return 0;
+    if ((n && !d_polys) || !points || !d_out) return TF21_E_BAD_ARG;
+    if (n_points > 0x7fffffffull || n_polys > 65535) return TF21_E_LEN_TOO_LARGE;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<u64> vals(n_points * width);
+    for (u64 i = 0; i < vals.size(); i++) vals[i] = hgl_from_raw(points[i]);  // canonical values of the points
+    Scratch dpts(st);
+    TF21_TRY(dpts.alloc(vals.size()));
+    TF21_CUDA(cudaMemcpyAsync(dpts.p, vals.data(), vals.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    dim3 grid((unsigned)n_points, (unsigned)n_polys);
+    if (width == 1)
+        TF21_LAUNCH_NAMED("poly_eval_kernel", poly_eval_kernel<1>, grid, kEvalThreads, 0, st, d_polys, n, dpts.p, (u32)n_points, d_out);
+    else
+        TF21_LAUNCH_NAMED("poly_eval_kernel", poly_eval_kernel<3>, grid, kEvalThreads, 0, st, d_polys, n, dpts.p, (u32)n_points, d_out);
+    return 0;
+}
+
+// Polynomial::par_batch_coset_extrapolate (polynomial.rs:2255-2331): every codeword is interpolated on the coset
+// (batched iNTT with offset^-i n^-1 fused into its last pass) and evaluated in every point.  The reference picks
+// between two algorithms by the number of points; both compute the values of the unique interpolant.
+int tf21_batch_coset_extrapolate_dev(uint64_t offset_raw, uint64_t codeword_length, const uint64_t *d_codewords,
+                                     uint64_t n_codewords, uint32_t width, const uint64_t *points, uint64_t n_points,
+                                     uint64_t *d_out, tf21_stream_t stream) {
+    TF21_TRY(check_ntt_len(codeword_length, width));
+    if (codeword_length == 0) return TF21_E_BAD_ARG;
+    if (n_codewords == 0 || n_points == 0) return 0;
+    if (!d_codewords || !points || !d_out) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    cudaStream_t st = (cudaStream_t)stream;
+    const u64 n = codeword_length;
+    Scratch coeffs(st);
+    TF21_TRY(coeffs.alloc(n * width * n_codewords));
+    if (n == 1) {
+        TF21_CUDA(cudaMemcpyAsync(coeffs.p, d_codewords, n_codewords * width * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    } else {
+        u64 g_inv = hgl_inv(hgl_from_raw(offset_raw));
+        ScaleTab post;
+        TF21_TRY(split_locked(*t, g_inv, hgl_inv(n % GL_P), n, &post));
+        TF21_TRY(ntt_run_locked(*t, d_codewords, n, coeffs.p, n, width, n_codewords, 1, NO_SCALE, post, 0, st));
+    }
+    // y-dimension of the grid is limited to 65535 polynomials per launch
+    for (u64 first = 0; first < n_codewords; first += 65535) {
+        const u64 cnt = n_codewords - first < 65535 ? n_codewords - first : 65535;
+        TF21_TRY(tf21_poly_evaluate_batch_dev(coeffs.p + first * n * width, n, cnt, width, points, n_points,
+                                              d_out + first * n_points * width, stream));
+    }
+    return 0;
+}
+
+int tf21_batch_coset_extrapolate(uint64_t offset_raw, uint64_t codeword_length, const uint64_t *codewords,
+                                 uint64_t n_codewords, uint32_t width, const uint64_t *points, uint64_t n_points,
+                                 uint64_t *out) {
+    TF21_TRY(check_ntt_len(codeword_length, width));
+    if (codeword_length == 0) return TF21_E_BAD_ARG;
+    if (n_codewords == 0 || n_points == 0) return 0;
+    if (!codewords || !points || !out) return TF21_E_BAD_ARG;
+    DevBuf dc, dout;
+    const u64 words = codeword_length * width * n_codewords;
+    TF21_TRY(dc.alloc(words));
+    TF21_TRY(dout.alloc(n_codewords * n_points * width));
+    TF21_CUDA(cudaMemcpy(dc.p, codewords, words * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(tf21_batch_coset_extrapolate_dev(offset_raw, codeword_length, dc.p, n_codewords, width, points, n_points,
+                                              dout.p, nullptr));
+    TF21_CUDA(cudaMemcpy(out, dout.p, n_codewords * n_points * width * sizeof(u64), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -517,6 +610,24 @@ int tf21_tip5_hash_columns_dev(const uint64_t *d_cols, uint64_t n_rows, uint64_t
     DeviceTables *t;
     TF21_TRY(get_tables(&t));
     return launch_hash_rows(d_cols, n_cols, n_rows, 1, col_stride_words, d_out, (cudaStream_t)stream);
+}
+
+// Tip5::sample_indices (tip5/mod.rs:636-656) on a sponge state held by the caller (16 raw words, updated)
+int tf21_tip5_sample_indices(uint64_t *state, uint32_t upper_bound, uint64_t num_indices, uint32_t *out) {
+    if (upper_bound == 0 || (upper_bound & (upper_bound - 1))) return TF21_E_LEN_NOT_POW2;  // assert!(is_power_of_two)
+    if (!state || (num_indices && !out)) return TF21_E_BAD_ARG;
+    if (num_indices == 0) return 0;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    DevBuf ds, dout;
+    TF21_TRY(ds.alloc(16));
+    TF21_TRY(dout.alloc((num_indices + 1) / 2));
+    TF21_CUDA(cudaMemcpy(ds.p, state, 16 * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_LAUNCH(tip5_sample_indices_kernel, 1, 32, 0, (cudaStream_t) nullptr, ds.p, upper_bound, num_indices,
+                hgl_inv(GL_EPS), (u32 *)dout.p);
+    TF21_CUDA(cudaMemcpy(out, dout.p, num_indices * sizeof(u32), cudaMemcpyDeviceToHost));
+    TF21_CUDA(cudaMemcpy(state, ds.p, 16 * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int tf21_tip5_permute(uint64_t *states, uint64_t count) {

@@ -260,6 +260,34 @@ __global__ void __launch_bounds__(32) mmr_bag_peaks_kernel(const u64 *__restrict
     for (int j = 0; j < TIP5_DIGEST; j++) out[j] = gl_canon(s[j]);
 }
 
+// Tip5::sample_indices (tip5/mod.rs:636-656): squeeze (emit state[0..10), then permute) until num_indices
+// elements other than BFieldElement::MAX have been seen; index = value as u32 % upper_bound (a power of two).
+// A sequential sponge walk -- one thread.  state: 16 raw words, updated in place like `&mut self`.
+__global__ void __launch_bounds__(32) tip5_sample_indices_kernel(u64 *__restrict__ state, u32 upper_bound, u64 num_indices,
+                                                                 u64 rinv, u32 *__restrict__ out) {
+    __shared__ uint8_t s_lut[256];
+    tip5_load_lut(s_lut);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    u64 s[TIP5_STATE];
+#pragma unroll
+    for (int k = 0; k < TIP5_STATE; k++) s[k] = state[k];
+    u64 produced = 0;
+    while (produced < num_indices) {
+        u64 buf[TIP5_RATE];
+#pragma unroll
+        for (int k = 0; k < TIP5_RATE; k++) buf[k] = gl_canon(s[k]);
+        tip5_permutation(s, s_lut);
+#pragma unroll
+        for (int k = 0; k < TIP5_RATE; k++) {
+            const u64 value = gl_mulc(buf[k], rinv);  // BFieldElement::value(): raw * 2^-64 mod p
+            if (produced < num_indices && value != GL_P - 1) out[produced++] = (u32)value & (upper_bound - 1);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TIP5_STATE; k++) state[k] = gl_canon(s[k]);
+}
+
 inline unsigned grid_for(u64 count, int threads) { return (unsigned)((count + threads - 1) / threads); }
 
 inline int launch_permute(u64 *d_states, u64 count, cudaStream_t st) {

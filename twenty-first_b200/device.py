@@ -98,6 +98,17 @@ def mmr_bag_peaks(peaks: torch.Tensor, leaf_count: int, out: torch.Tensor) -> No
     B.check(B.lib.tf21_mmr_bag_peaks_dev(_p(peaks), peaks.numel() // 5, leaf_count, _p(out), _stream()))
 
 
+def batch_coset_extrapolate(offset_raw: int, codeword_length: int, codewords: torch.Tensor, width: int, points,
+                            out: torch.Tensor) -> None:
+    """points: numpy uint64 host array of raw words (n_points * width)"""
+    import numpy as np
+
+    pts = np.ascontiguousarray(points, dtype=np.uint64)
+    n_cw = codewords.numel() // (codeword_length * width)
+    B.check(B.lib.tf21_batch_coset_extrapolate_dev(offset_raw, codeword_length, _p(codewords), n_cw, width,
+                                                   pts.ctypes.data, pts.size // width, _p(out), _stream()))
+
+
 def kernel_launch_count() -> int:
     return int(B.lib.tf21_kernel_launch_count())
 
