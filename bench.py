@@ -52,7 +52,34 @@ class ClockSampler:
         self.stop = threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
 
+    def _run_nvml(self) -> bool:
+        """fast path: NVML in-process (a sample every ~2 ms, so that even a 50 ms timed region is covered)"""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [("nvmlClocksThrottleReasonHwSlowdown", 0x8), ("nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    ("nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), ("nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+            masks = [getattr(nv, name, default) for name, default in bits]
+        except Exception:
+            return False
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = get_reasons(h)
+                self.samples.append([str(sm), str(mx)] + ["Active" if r & m else "Not Active" for m in masks])
+            except Exception:
+                pass
+            self.stop.wait(0.002)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            return
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",

@@ -80,6 +80,11 @@ inline int upload_tip5_constants() {
         to_seeds(hi + r * TIP5_STATE);
     }
 #endif
+    {
+        u64 raw[TIP5_ROUNDS * TIP5_STATE];
+        for (int i = 0; i < TIP5_ROUNDS * TIP5_STATE; i++) raw[i] = hgl_to_raw(kTip5RoundConstants[i]);
+        TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc_raw, raw, sizeof(raw)));
+    }
     TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc0f_lo, lo0, sizeof(lo0)));
     TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc0f_hi, hi0, sizeof(hi0)));
     uint8_t lut[256];
@@ -143,24 +148,46 @@ __global__ void __launch_bounds__(kTip5Threads, TIP5_MIN_BLOCKS)
     for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
 }
 
+// ---- cooperative kernels for the top of a Merkle tree (tip5_permutation_coop, tip5.cuh) ----------------
+__device__ __forceinline__ void tip5_coop_setup(uint8_t *s_lut, u64 *s_rc) {
+    tip5_load_lut(s_lut);
+    for (int i = threadIdx.x; i < TIP5_ROUNDS * TIP5_STATE; i += blockDim.x) s_rc[i] = c_tip5_rc_raw[i];
+}
+
+// hash_pair of node pair i of a level: 16 lanes, lane l < 10 loads word l, lanes 10..15 hold ONE
+__device__ __forceinline__ void tip5_coop_hash10(const u64 *__restrict__ in, u64 *__restrict__ out, u32 lane16,
+                                                 const uint8_t *s_lut, const u64 *s_rc) {
+    u64 s = lane16 < TIP5_RATE ? in[lane16] : TIP5_RAW_ONE;
+    s = tip5_permutation_coop(s, lane16, s_lut, s_rc);
+    if (lane16 < TIP5_DIGEST) out[lane16] = s;
+}
+
+constexpr int kCoopThreads = 128;  // 8 hashes per CTA
+__global__ void __launch_bounds__(kCoopThreads) tip5_hash10_coop_kernel(const u64 *__restrict__ in, u64 count,
+                                                                        u64 *__restrict__ out) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ u64 s_rc[TIP5_ROUNDS * TIP5_STATE];
+    tip5_coop_setup(s_lut, s_rc);
+    __syncthreads();
+    const u64 h = ((u64)blockIdx.x * kCoopThreads + threadIdx.x) >> 4;
+    // whole 16-lane groups leave together (count is not necessarily a multiple of 8), the shuffles inside a
+    // group only name lanes of the group
+    if (h >= count) return;
+    tip5_coop_hash10(in + 10 * h, out + 5 * h, threadIdx.x & 15, s_lut, s_rc);
+}
+
 // Top of a Merkle tree in one CTA: levels with cnt = first_cnt, first_cnt/2, ..., 1.
 // nodes: heap-indexed array; the children level (2*first_cnt nodes) is already complete.
-constexpr int kMerkleTailThreads = 256;
+constexpr int kMerkleTailThreads = 1024;  // 64 cooperative hashes in flight
 __global__ void __launch_bounds__(kMerkleTailThreads) merkle_tail_kernel(u64 *nodes, u32 first_cnt) {
     __shared__ uint8_t s_lut[256];
-    tip5_load_lut(s_lut);
+    __shared__ u64 s_rc[TIP5_ROUNDS * TIP5_STATE];
+    tip5_coop_setup(s_lut, s_rc);
     __syncthreads();
+    const u32 group = threadIdx.x >> 4, lane16 = threadIdx.x & 15;
     for (u32 cnt = first_cnt; cnt >= 1; cnt >>= 1) {
-        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) {
-            u64 s[TIP5_STATE];
-            const u64 *src = nodes + 10ull * (cnt + i);
-#pragma unroll
-            for (int k = 0; k < TIP5_RATE; k++) s[k] = src[k];
-            tip5_permutation<true>(s, s_lut);
-            u64 *dst = nodes + 5ull * (cnt + i);
-#pragma unroll
-            for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
-        }
+        for (u32 i = group; i < cnt; i += kMerkleTailThreads / 16)
+            tip5_coop_hash10(nodes + 10ull * (cnt + i), nodes + 5ull * (cnt + i), lane16, s_lut, s_rc);
         __threadfence_block();
         __syncthreads();
     }
@@ -319,13 +346,22 @@ inline int launch_hash_rows(const u64 *d_data, u64 row_len, u64 n_rows, u64 row_
     return 0;
 }
 
-constexpr u32 kMerkleTailCnt = 256;  // levels with <= this many nodes are finished by one CTA
+constexpr u32 kMerkleTailCnt = 128;    // levels with <= this many nodes are finished by one CTA
+#ifndef TF21_MERKLE_COOP_CNT
+#define TF21_MERKLE_COOP_CNT 4096
+#endif
+constexpr u32 kMerkleCoopCnt = TF21_MERKLE_COOP_CNT;  // levels with <= this many nodes use 16 lanes per hash (latency bound)
 
 // fills nodes[1..n) given nodes[n..2n) (sequentially_fill_tree, merkle_tree.rs:216-222, level-batched)
 inline int launch_merkle_levels(u64 *d_nodes, u64 n_leafs, cudaStream_t st) {
     u64 cnt = n_leafs / 2;
     while (cnt > kMerkleTailCnt) {
-        TF21_TRY(launch_hash10(d_nodes + 10 * cnt, cnt, d_nodes + 5 * cnt, st));
+        if (cnt > kMerkleCoopCnt) {
+            TF21_TRY(launch_hash10(d_nodes + 10 * cnt, cnt, d_nodes + 5 * cnt, st));
+        } else {
+            TF21_LAUNCH(tip5_hash10_coop_kernel, grid_for(16 * cnt, kCoopThreads), kCoopThreads, 0, st,
+                        d_nodes + 10 * cnt, cnt, d_nodes + 5 * cnt);
+        }
         cnt >>= 1;
     }
     if (cnt >= 1) {
