@@ -312,7 +312,7 @@ def test_tip5_hash_varlen_and_rows_match_oracle(tf, oracle):
     for length in (0, 1, 9, 10, 11, 19, 20, 21, 100, 16384):
         x = rnd(800 + length, length)
         assert np.array_equal(tf.Tip5.hash_varlen(x), oracle.hash_varlen(x)), length
-    for row_len, n_rows in ((1, 7), (10, 130), (33, 257), (0, 3)):
+    for row_len, n_rows in ((1, 7), (10, 130), (33, 257), (0, 3), (25, 4097), (7, 20000)):  # <= 4096 rows: 16 lanes per row
         rows = rnd(900 + row_len, row_len * n_rows).reshape(n_rows, row_len)
         got = tf.Tip5.hash_rows(rows)
         for r in range(0, n_rows, max(1, n_rows // 9)):
@@ -401,7 +401,7 @@ def test_tip5_hash_columns_matches_row_hashing(tf, oracle):
 
     dev = importlib.import_module("twenty-first_b200.device")
     cuda = torch.device("cuda:0")
-    for n_rows, n_cols in ((1, 1), (257, 7), (1024, 10), (4096, 33)):
+    for n_rows, n_cols in ((1, 1), (257, 7), (1024, 10), (4096, 33), (8192, 21), (1 << 16, 4)):
         cols = rnd(0xC0 + n_cols, n_rows * n_cols).reshape(n_cols, n_rows)
         d_cols = torch.from_numpy(cols.view(np.int64)).to(cuda)
         out = torch.zeros(5 * n_rows, dtype=torch.int64, device=cuda)

@@ -96,6 +96,10 @@ inline int upload_tip5_constants() {
     return 0;
 }
 
+#ifndef TF21_MERKLE_COOP_CNT
+#define TF21_MERKLE_COOP_CNT 4096
+#endif
+constexpr u32 kMerkleCoopCnt = TF21_MERKLE_COOP_CNT;  // batches (Merkle levels, rows) with <= this many nodes use 16 lanes per hash (latency bound)
 constexpr int kTip5Threads = 128;
 #ifndef TIP5_MIN_BLOCKS
 #define TIP5_MIN_BLOCKS 4  /* resident CTAs per SM the register allocation aims for (A/B: tools/ab.sh) */
@@ -229,6 +233,36 @@ __global__ void __launch_bounds__(kTip5Threads)
     for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
 }
 
+// Cooperative form of the same sponge for few long rows (Tip5::hash_varlen of one sequence is a chain of
+// dependent permutations): 16 lanes per row, lane l < 10 overwrites its rate element per chunk.
+__global__ void __launch_bounds__(kCoopThreads)
+    tip5_hash_rows_coop_kernel(const u64 *__restrict__ data, u64 row_len, u64 n_rows, u64 row_stride, u64 elem_stride,
+                               u64 *__restrict__ out) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ u64 s_rc[TIP5_ROUNDS * TIP5_STATE];
+    tip5_coop_setup(s_lut, s_rc);
+    __syncthreads();
+    const u64 i = ((u64)blockIdx.x * kCoopThreads + threadIdx.x) >> 4;
+    if (i >= n_rows) return;
+    const u32 lane16 = threadIdx.x & 15;
+    const u64 *row = data + i * row_stride;
+    u64 s = 0;
+    const u64 full = row_len / TIP5_RATE;
+    for (u64 c = 0; c < full; c++) {
+        if (lane16 < TIP5_RATE) s = row[(c * TIP5_RATE + lane16) * elem_stride];
+        s = tip5_permutation_coop(s, lane16, s_lut, s_rc);
+    }
+    const u32 rem = (u32)(row_len - full * TIP5_RATE);
+    if (lane16 < TIP5_RATE) {
+        u64 v = 0;
+        if (lane16 < rem) v = row[(full * TIP5_RATE + lane16) * elem_stride];
+        if (lane16 == rem) v = TIP5_RAW_ONE;
+        s = v;
+    }
+    s = tip5_permutation_coop(s, lane16, s_lut, s_rc);
+    if (lane16 < TIP5_DIGEST) out[5 * i + lane16] = s;
+}
+
 // nodes[0] = 0 and nodes[n..2n) = leafs  (initialize_merkle_tree_nodes, merkle_tree.rs:393-429)
 __global__ void merkle_init_kernel(const u64 *__restrict__ leafs, u64 n_leaf_words, u64 *__restrict__ nodes) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,26 +299,23 @@ __global__ void merkle_gather_kernel(const u64 *__restrict__ nodes, const u64 *_
 __global__ void __launch_bounds__(32) mmr_bag_peaks_kernel(const u64 *__restrict__ peaks, u32 n_peaks, u64 lc_lo_raw,
                                                            u64 lc_hi_raw, u64 *__restrict__ out) {
     __shared__ uint8_t s_lut[256];
-    tip5_load_lut(s_lut);
+    __shared__ u64 s_rc[TIP5_ROUNDS * TIP5_STATE];
+    tip5_coop_setup(s_lut, s_rc);
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    u64 s[TIP5_STATE];
-    s[0] = lc_lo_raw;
-    s[1] = lc_hi_raw;
-#pragma unroll
-    for (int k = 2; k < TIP5_RATE; k++) s[k] = 0;
-    tip5_permutation<true>(s, s_lut);
+    if (threadIdx.x >= 16) return;
+    const u32 lane16 = threadIdx.x;
+    // 16 lanes = the 16 state elements (tip5_permutation_coop): hash_10(lo, hi, 0 x 8), capacity = ONE
+    u64 s = lane16 == 0 ? lc_lo_raw : lane16 == 1 ? lc_hi_raw : lane16 < TIP5_RATE ? 0ull : TIP5_RAW_ONE;
+    s = tip5_permutation_coop(s, lane16, s_lut, s_rc);
 #pragma unroll 1
     for (u32 k = n_peaks; k-- > 0;) {
-#pragma unroll
-        for (int j = 0; j < TIP5_DIGEST; j++) {
-            s[TIP5_DIGEST + j] = gl_canon(s[j]);
-            s[j] = peaks[5 * k + j];
-        }
-        tip5_permutation<true>(s, s_lut);
+        // hash_pair(peak, acc): lanes 0..4 <- peak, lanes 5..9 <- acc (= lanes 0..4 of the previous state)
+        const u32 lo = __shfl_sync(0xffffu, (u32)s, (lane16 + 11) & 15, 16);
+        const u32 hi = __shfl_sync(0xffffu, (u32)(s >> 32), (lane16 + 11) & 15, 16);
+        s = lane16 < TIP5_DIGEST ? peaks[5 * k + lane16] : lane16 < TIP5_RATE ? gl_pack(lo, hi) : TIP5_RAW_ONE;
+        s = tip5_permutation_coop(s, lane16, s_lut, s_rc);
     }
-#pragma unroll
-    for (int j = 0; j < TIP5_DIGEST; j++) out[j] = gl_canon(s[j]);
+    if (lane16 < TIP5_DIGEST) out[lane16] = s;
 }
 
 // Tip5::sample_indices (tip5/mod.rs:636-656): squeeze (emit state[0..10), then permute) until num_indices
@@ -293,26 +324,24 @@ __global__ void __launch_bounds__(32) mmr_bag_peaks_kernel(const u64 *__restrict
 __global__ void __launch_bounds__(32) tip5_sample_indices_kernel(u64 *__restrict__ state, u32 upper_bound, u64 num_indices,
                                                                  u64 rinv, u32 *__restrict__ out) {
     __shared__ uint8_t s_lut[256];
-    tip5_load_lut(s_lut);
+    __shared__ u64 s_rc[TIP5_ROUNDS * TIP5_STATE];
+    tip5_coop_setup(s_lut, s_rc);
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    u64 s[TIP5_STATE];
-#pragma unroll
-    for (int k = 0; k < TIP5_STATE; k++) s[k] = state[k];
+    if (threadIdx.x >= 16) return;
+    const u32 lane16 = threadIdx.x;
+    u64 s = state[lane16];
     u64 produced = 0;
     while (produced < num_indices) {
-        u64 buf[TIP5_RATE];
-#pragma unroll
-        for (int k = 0; k < TIP5_RATE; k++) buf[k] = gl_canon(s[k]);
-        tip5_permutation(s, s_lut);
-#pragma unroll
-        for (int k = 0; k < TIP5_RATE; k++) {
-            const u64 value = gl_mulc(buf[k], rinv);  // BFieldElement::value(): raw * 2^-64 mod p
-            if (produced < num_indices && value != GL_P - 1) out[produced++] = (u32)value & (upper_bound - 1);
-        }
+        // squeeze: lanes 0..9 hold the produced elements, then the state is permuted (tip5/mod.rs:693-698)
+        const u64 value = gl_mulc(gl_canon(s), rinv);  // BFieldElement::value(): raw * 2^-64 mod p
+        const bool keep = lane16 < TIP5_RATE && value != GL_P - 1;
+        const u32 kept = __ballot_sync(0xffffu, keep) & 0x3ffu;
+        const u64 pos = produced + __popc(kept & ((1u << lane16) - 1));
+        if (keep && pos < num_indices) out[pos] = (u32)value & (upper_bound - 1);
+        produced += __popc(kept);
+        s = tip5_permutation_coop(s, lane16, s_lut, s_rc);
     }
-#pragma unroll
-    for (int k = 0; k < TIP5_STATE; k++) state[k] = gl_canon(s[k]);
+    state[lane16] = gl_canon(s);
 }
 
 inline unsigned grid_for(u64 count, int threads) { return (unsigned)((count + threads - 1) / threads); }
@@ -341,16 +370,17 @@ inline int launch_hash10_copy(const u64 *d_in, u64 count, u64 *d_out, u64 *d_cop
 inline int launch_hash_rows(const u64 *d_data, u64 row_len, u64 n_rows, u64 row_stride, u64 elem_stride,
                             u64 *d_out, cudaStream_t st) {
     if (n_rows == 0) return 0;
+    if (n_rows <= kMerkleCoopCnt) {  // latency bound: 16 lanes per row
+        TF21_LAUNCH(tip5_hash_rows_coop_kernel, grid_for(16 * n_rows, kCoopThreads), kCoopThreads, 0, st, d_data, row_len,
+                    n_rows, row_stride, elem_stride, d_out);
+        return 0;
+    }
     TF21_LAUNCH(tip5_hash_rows_kernel, grid_for(n_rows, kTip5Threads), kTip5Threads, 0, st, d_data, row_len,
                 n_rows, row_stride, elem_stride, d_out);
     return 0;
 }
 
 constexpr u32 kMerkleTailCnt = 128;    // levels with <= this many nodes are finished by one CTA
-#ifndef TF21_MERKLE_COOP_CNT
-#define TF21_MERKLE_COOP_CNT 4096
-#endif
-constexpr u32 kMerkleCoopCnt = TF21_MERKLE_COOP_CNT;  // levels with <= this many nodes use 16 lanes per hash (latency bound)
 
 // fills nodes[1..n) given nodes[n..2n) (sequentially_fill_tree, merkle_tree.rs:216-222, level-batched)
 inline int launch_merkle_levels(u64 *d_nodes, u64 n_leafs, cudaStream_t st) {
