@@ -34,7 +34,7 @@ def rand_words(n):
     return x
 
 
-what = sys.argv[1:] or ["ntt", "merkle", "tip5", "lde"]
+what = sys.argv[1:] or ["ntt", "merkle", "tip5", "rows", "lde"]
 if "ntt" in what:
     for log2n, batch in ((10, 65536), (16, 1024), (20, 64), (20, 256), (24, 8)):
         x = rand_words((1 << log2n) * batch)
@@ -58,6 +58,14 @@ if "tip5" in what:
     out = torch.zeros(5 * n, dtype=torch.int64, device=cuda)
     best, med = timeit(lambda: dev.tip5_hash_10(inp, out))
     print(f"hash_10 x2^22: best {best:.3f} ms  {n/best*1e3/1e9:.3f} G hash/s")
+if "rows" in what:
+    n_rows, n_cols = 1 << 20, 100
+    cols = rand_words(n_rows * n_cols)
+    out = torch.zeros(5 * n_rows, dtype=torch.int64, device=cuda)
+    best, med = timeit(lambda: dev.tip5_hash_columns(cols, n_rows, n_cols, out), iters=3, warm=1)
+    perms = n_rows * ((n_cols + 1 + 9) // 10)
+    print(f"hash_columns 2^20 rows x {n_cols} cols: best {best:.3f} ms  {perms/best*1e3/1e9:.3f} G permutations/s  "
+          f"{8*n_rows*n_cols/best/1e6:.0f} GB/s read")
 if "lde" in what:
     for li, lo in ((18, 22), (22, 26)):
         vals = rand_words(3 << li)

@@ -163,7 +163,10 @@ struct FastColArgs {
     ScaleTab pre;
 };
 
-template <bool INV>
+// PLAIN: every input row exists (n_in == n), no coset pre-scale and the inter-pass twiddles come from the full
+// table -- the batched 2^20 transform.  The staging loops then carry no index arithmetic or uniform branches
+// (ncu: ~890 of 5300 instructions per warp and most `no_instruction` stalls of the general form were staging).
+template <bool INV, bool PLAIN>
 __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kernel(const FastColArgs a) {
     extern __shared__ u64 smem[];
     u64 *tile = smem;
@@ -184,13 +187,17 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
 #pragma unroll 8
         for (u32 it = 0; it < 32; it++) {
             const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
-            const u64 j = ((u64)o * 1024 + r) * inner_elems + jcol;
-            u64 x = 0;
-            if (j < a.n_in_elems) {
-                x = src[(u64)r * a.inner_words];
-                if (a.pre.lo) x = gl_mul(x, scale_factor(a.pre, j));
+            if constexpr (PLAIN) {
+                tl[r] = src[(u64)r * a.inner_words];
+            } else {
+                const u64 j = ((u64)o * 1024 + r) * inner_elems + jcol;
+                u64 x = 0;
+                if (j < a.n_in_elems) {
+                    x = src[(u64)r * a.inner_words];
+                    if (a.pre.lo) x = gl_mul(x, scale_factor(a.pre, j));
+                }
+                tl[r] = x;
             }
-            tl[r] = x;
         }
     }
     __syncthreads();
@@ -202,8 +209,9 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
     for (int aa = 0; aa < 32; aa++) v[aa] = slice[32 * aa + lane];
     const u64 jrest = (q0 + warp) / a.w;
     // inter-pass twiddle omega_B^(i * j_rest), i = lane + 32 k2: straight from the full table when there is one
-    dft1024_warp<INV, true, TF21_SHL_COL>(v, slice, a.t1 + lane, a.tw_full ? a.tw_full + jrest * 1024 + lane : nullptr, lane);
-    if (!a.tw_full) {
+    dft1024_warp<INV, true, TF21_SHL_COL>(v, slice, a.t1 + lane,
+                                          (PLAIN || a.tw_full) ? a.tw_full + jrest * 1024 + lane : nullptr, lane);
+    if (!PLAIN && !a.tw_full) {
         const u64 bmask = (1ull << a.log_b) - 1;
 #pragma unroll 4
         for (int k2 = 0; k2 < 32; k2++) {
@@ -245,7 +253,9 @@ struct FastRowArgs {
 // o' + rows * i_k with o' = i_1 + n1 (i_2 + n2 i_3) (digit reversal of the row index).  A CTA takes 8
 // consecutive word-columns tc = o' * w + c of the output; a warp loads its row directly (stride w),
 // the transposed store goes through shared memory; canonical on store.
-template <bool INV, u32 W>
+// POST: a scalar and / or a coset scale table is applied on store (unscale of short inverse transforms,
+// fast_coset_interpolate); without it the stage-out loop has no uniform branches.
+template <bool INV, u32 W, bool POST>
 __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kernel(const FastRowArgs a) {
     extern __shared__ u64 smem[];
     u64 *tile = smem;
@@ -295,8 +305,10 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kern
         for (u32 it = 0; it < 32; it++) {
             const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
             u64 x = tl[r];
-            if (a.post_scalar) x = gl_mul(x, a.post_scalar);
-            if (a.post.lo) x = gl_mul(x, scale_factor_l(a.post, op + (u64)rows * r));
+            if constexpr (POST) {
+                if (a.post_scalar) x = gl_mul(x, a.post_scalar);
+                if (a.post.lo) x = gl_mul(x, scale_factor_l(a.post, op + (u64)rows * r));
+            }
             dst[(u64)r * ostride] = gl_canonw(x);
         }
     }
@@ -883,10 +895,14 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
             a.pre = cur_pre;
             u64 grid = batch * n_outer * a.n_col_tiles;
             if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
-            if (inverse)
-                TF21_TRY(launch_fast(ntt1024_col_kernel<true>, (unsigned)grid, a, st));
-            else
-                TF21_TRY(launch_fast(ntt1024_col_kernel<false>, (unsigned)grid, a, st));
+            const bool plain = cur_n_in == n && !cur_pre.lo && tw_full != nullptr;
+            if (inverse) {
+                if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, true>), (unsigned)grid, a, st));
+                else TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, false>), (unsigned)grid, a, st));
+            } else {
+                if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, true>), (unsigned)grid, a, st));
+                else TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, false>), (unsigned)grid, a, st));
+            }
         } else {
             SmallColArgs a{};
             a.src = cur_src;
@@ -934,12 +950,18 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     a.post = post;
     u64 grid = (a.n_cols_total + kFastCols - 1) / kFastCols;
     if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+    const bool has_post = post_scalar != 0 || post.lo != nullptr;
+#define TF21_ROW_LAUNCH(I_, W_, P_) \
+    return launch_fast_named("ntt1024_row_kernel", (ntt1024_row_kernel<I_, W_, P_>), (unsigned)grid, a, st)
     if (w == 1) {
-        if (inverse) return launch_fast_named("ntt1024_row_kernel", ntt1024_row_kernel<true, 1>, (unsigned)grid, a, st);
-        return launch_fast_named("ntt1024_row_kernel", ntt1024_row_kernel<false, 1>, (unsigned)grid, a, st);
+        if (inverse) { if (has_post) TF21_ROW_LAUNCH(true, 1, true); TF21_ROW_LAUNCH(true, 1, false); }
+        if (has_post) TF21_ROW_LAUNCH(false, 1, true);
+        TF21_ROW_LAUNCH(false, 1, false);
     }
-    if (inverse) return launch_fast_named("ntt1024_row_kernel", ntt1024_row_kernel<true, 3>, (unsigned)grid, a, st);
-    return launch_fast_named("ntt1024_row_kernel", ntt1024_row_kernel<false, 3>, (unsigned)grid, a, st);
+    if (inverse) { if (has_post) TF21_ROW_LAUNCH(true, 3, true); TF21_ROW_LAUNCH(true, 3, false); }
+    if (has_post) TF21_ROW_LAUNCH(false, 3, true);
+    TF21_ROW_LAUNCH(false, 3, false);
+#undef TF21_ROW_LAUNCH
 }
 
 }  // namespace tf21

@@ -47,12 +47,20 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
                                        (int)t.smem_optin));
         TF21_CUDA(cudaFuncSetAttribute(ntt_row_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)t.smem_optin));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+#define TF21_FAST_SMEM(K) TF21_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem))
+        TF21_FAST_SMEM((ntt1024_col_kernel<false, false>));
+        TF21_FAST_SMEM((ntt1024_col_kernel<false, true>));
+        TF21_FAST_SMEM((ntt1024_col_kernel<true, false>));
+        TF21_FAST_SMEM((ntt1024_col_kernel<true, true>));
+        TF21_FAST_SMEM((ntt1024_row_kernel<false, 1, false>));
+        TF21_FAST_SMEM((ntt1024_row_kernel<false, 1, true>));
+        TF21_FAST_SMEM((ntt1024_row_kernel<true, 1, false>));
+        TF21_FAST_SMEM((ntt1024_row_kernel<true, 1, true>));
+        TF21_FAST_SMEM((ntt1024_row_kernel<false, 3, false>));
+        TF21_FAST_SMEM((ntt1024_row_kernel<false, 3, true>));
+        TF21_FAST_SMEM((ntt1024_row_kernel<true, 3, false>));
+        TF21_FAST_SMEM((ntt1024_row_kernel<true, 3, true>));
+#undef TF21_FAST_SMEM
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
