@@ -184,8 +184,21 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
         const u64 *src = a.src + (u64)b * a.src_array_words + block_off + c;
         const u64 jcol = (q0 + c) / a.w;
         u64 *tl = tile + c * kFastS;
+        if constexpr (PLAIN) {
+            // asynchronous global -> shared copies (LDGSTS): all 32 rows of a lane are in flight at once and no
+            // register round trip; the column pass was waiting on this staging (long_scoreboard 1.35 per issue)
+            const u32 tl_s = (u32)__cvta_generic_to_shared(tl);
+#pragma unroll
+            for (u32 it = 0; it < 32; it++) {
+                const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tl_s + r * 8u),
+                             "l"(src + (u64)r * a.inner_words)
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        }
 #pragma unroll 8
-        for (u32 it = 0; it < 32; it++) {
+        for (u32 it = 0; it < (PLAIN ? 0u : 32u); it++) {
             const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
             if constexpr (PLAIN) {
                 tl[r] = src[(u64)r * a.inner_words];
