@@ -37,7 +37,7 @@ namespace tf21 {
 #define TF21_SHL_ROW TF21_SHL_WIDE
 #endif
 #ifndef TF21_FAST_COLS
-#define TF21_FAST_COLS 8
+#define TF21_FAST_COLS 4  /* 4 CTAs of 128 threads per SM: finer interleaving of staging and compute phases than 2 x 256 (tools/ab.sh: 3.14 ms against 3.27 ms per 256-column batch once the staging is asynchronous; 32-byte row segments = one DRAM sector) */
 #endif
 constexpr u32 kFastCols = TF21_FAST_COLS;  // word-columns (= warps) per CTA: 4, 8 or 16
 // u64 per column slice in shared memory (>= 32 * 33), chosen so that the staging pattern
