@@ -171,18 +171,21 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
     extern __shared__ u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 ct = blockIdx.x % a.n_col_tiles;
-    const u32 rest = blockIdx.x / a.n_col_tiles;
-    const u32 o = rest % a.n_outer, b = rest / a.n_outer;
+    // grid = (column tiles, outer blocks, arrays of the batch): no index divisions
+    const u32 ct = blockIdx.x, o = blockIdx.y, b = blockIdx.z;
     const u64 q0 = (u64)ct * kFastCols;
-    const u64 inner_elems = a.inner_words / a.w;
+    const u64 inner_elems = a.w == 1 ? (u32)a.inner_words : (u32)a.inner_words / 3u;
     const u32 c = lane % kFastCols, rsub = lane / kFastCols;
+    // a tile spans 1024 * inner_words words; inner_words = 1024 w in every plan (the column pass always works on
+    // 2^20-point blocks), so row offsets fit 32 bits: one narrow IMAD per row instead of a 64-bit multiply
+    const u32 row_words = (u32)a.inner_words;
 
     // ---- stage in: 8 lanes per 64-byte row segment, 4 rows per warp instruction ----
     const u64 block_off = (u64)o * 1024 * a.inner_words + q0;
     {
         const u64 *src = a.src + (u64)b * a.src_array_words + block_off + c;
-        const u64 jcol = (q0 + c) / a.w;
+        const u32 qc = (u32)q0 + c;
+        const u64 jcol = a.w == 1 ? qc : qc / 3u;
         u64 *tl = tile + c * kFastS;
         if constexpr (PLAIN) {
             // asynchronous global -> shared copies (LDGSTS): all 32 rows of a lane are in flight at once and no
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
             for (u32 it = 0; it < 32; it++) {
                 const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tl_s + r * 8u),
-                             "l"(src + (u64)r * a.inner_words)
+                             "l"(src + r * row_words)
                              : "memory");
             }
             asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -201,12 +204,12 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
         for (u32 it = 0; it < (PLAIN ? 0u : 32u); it++) {
             const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
             if constexpr (PLAIN) {
-                tl[r] = src[(u64)r * a.inner_words];
+                tl[r] = src[r * row_words];
             } else {
                 const u64 j = ((u64)o * 1024 + r) * inner_elems + jcol;
                 u64 x = 0;
                 if (j < a.n_in_elems) {
-                    x = src[(u64)r * a.inner_words];
+                    x = src[r * row_words];
                     if (a.pre.lo) x = gl_mul(x, scale_factor(a.pre, j));
                 }
                 tl[r] = x;
@@ -220,7 +223,8 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
     u64 v[32];
 #pragma unroll
     for (int aa = 0; aa < 32; aa++) v[aa] = slice[32 * aa + lane];
-    const u64 jrest = (q0 + warp) / a.w;
+    const u32 qw = (u32)q0 + warp;  // < inner_words <= 2^21; w is 1 or 3: no run-time division
+    const u64 jrest = a.w == 1 ? qw : qw / 3u;
     // inter-pass twiddle omega_B^(i * j_rest), i = lane + 32 k2: straight from the full table when there is one
     dft1024_warp<INV, true, TF21_SHL_COL>(v, slice, a.t1 + lane,
                                           (PLAIN || a.tw_full) ? a.tw_full + jrest * 1024 + lane : nullptr, lane);
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
 #pragma unroll 8
         for (u32 it = 0; it < 32; it++) {
             const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
-            dst[(u64)r * a.inner_words] = tl[r];
+            dst[r * row_words] = tl[r];
         }
     }
 }
@@ -254,6 +258,7 @@ struct FastRowArgs {
     u64 array_words;      // n * w
     u32 w;
     u32 n1, n2, n3;       // sizes of the leading digits i_1, i_2, i_3 (1 when absent); rows = n1 n2 n3
+    u32 log_n1, log_n2;   // their logarithms (powers of two)
     u64 n_cols_total;     // batch * rows * w word-columns over the whole batch
     u32 n_tiles;          // rows * w / 8 when that is exact (a CTA never straddles arrays), else 0
     const u64 *t1;
@@ -275,29 +280,27 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kern
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 rows = a.n1 * a.n2 * a.n3;
     const u32 rw = rows * W;  // word-columns per array
-    // word-column g of the whole batch: array b = g / rw, column tc = g % rw.  A CTA takes 8 consecutive g
-    // (for rows * W < 8, i.e. n = 2^11 / 2^12, they span several arrays of the batch).
-    const u64 g0 = (u64)blockIdx.x * kFastCols;
-    // rows * W a multiple of 8 (every n >= 2^13): a CTA stays inside one array -- one 32-bit division per CTA
-    u64 b_cta = 0;
-    u32 tc_cta = 0;
-    if (a.n_tiles) {
-        b_cta = blockIdx.x / a.n_tiles;
-        tc_cta = (blockIdx.x - (u32)b_cta * a.n_tiles) * kFastCols;
-    }
+    // word-column g of the whole batch: array b = g / rw, column tc = g % rw.  A CTA takes kFastCols consecutive g.
+    // rows * W a multiple of kFastCols (every n >= 2^12): grid = (tiles per array, arrays), a CTA stays inside one
+    // array and needs no division; otherwise (n = 2^11, XFE 2^11) the columns of a CTA may span several arrays.
+    const bool tiled = a.n_tiles != 0;
+    const u64 g0 = tiled ? 0 : (u64)blockIdx.x * kFastCols;
+    const u64 b_cta = tiled ? blockIdx.y : 0;
+    const u32 tc_cta = tiled ? blockIdx.x * kFastCols : 0;
     {
         const u64 g = g0 + warp;
-        if (g < a.n_cols_total) {
-            const u64 b = a.n_tiles ? b_cta : g / rw;
-            const u32 tc = a.n_tiles ? tc_cta + warp : (u32)(g - b * rw);
+        if (tiled || g < a.n_cols_total) {
+            const u64 b = tiled ? b_cta : g / rw;
+            const u32 tc = tiled ? tc_cta + warp : (u32)(g - b * rw);
             const u32 op = tc / W, c = tc - op * W;
-            const u32 i1 = op % a.n1, r23 = op / a.n1;
-            const u32 i2 = r23 % a.n2, i3 = r23 / a.n2;
-            const u64 rho = ((u64)i1 * a.n2 + i2) * a.n3 + i3;
-            const u64 *row = a.src + b * a.array_words + rho * 1024 * W + c;
+            // n1, n2, n3 are powers of two (the sizes of the leading passes)
+            const u32 i1 = op & (a.n1 - 1), r23 = op >> a.log_n1;
+            const u32 i2 = r23 & (a.n2 - 1), i3 = r23 >> a.log_n2;
+            const u32 rho = (i1 * a.n2 + i2) * a.n3 + i3;  // < rows
+            const u64 *row = a.src + b * a.array_words + (u64)rho * (1024 * W) + c;
             u64 v[32];
 #pragma unroll
-            for (int aa = 0; aa < 32; aa++) v[aa] = row[(u64)(32 * aa + lane) * W];
+            for (int aa = 0; aa < 32; aa++) v[aa] = row[(32 * aa + lane) * W];
             dft1024_warp<INV, false, TF21_SHL_ROW>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane);
         }
     }
@@ -307,22 +310,37 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kern
     {
         const u32 c8 = lane % kFastCols, rsub = lane / kFastCols;
         const u64 g = g0 + c8;
-        if (g >= a.n_cols_total) return;
-        const u64 b = a.n_tiles ? b_cta : g / rw;
-        const u32 tc = a.n_tiles ? tc_cta + c8 : (u32)(g - b * rw);
+        if (!tiled && g >= a.n_cols_total) return;
+        const u64 b = tiled ? b_cta : g / rw;
+        const u32 tc = tiled ? tc_cta + c8 : (u32)(g - b * rw);
         u64 *dst = a.dst + b * a.array_words + tc;
         const u64 *tl = tile + c8 * kFastS;
-        const u64 ostride = (u64)rows * W;
-        const u64 op = tc / W;  // element index = op + rows * r
+        const u32 op = tc / W;  // element index = op + rows * r
+        if (a.array_words < (1ull << 29)) {
+            // byte offsets of an array below 4 GiB: 32-bit row offsets (one narrow IMAD per row)
+            const u32 ostride = rw;
 #pragma unroll 8
-        for (u32 it = 0; it < 32; it++) {
-            const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
-            u64 x = tl[r];
-            if constexpr (POST) {
-                if (a.post_scalar) x = gl_mul(x, a.post_scalar);
-                if (a.post.lo) x = gl_mul(x, scale_factor_l(a.post, op + (u64)rows * r));
+            for (u32 it = 0; it < 32; it++) {
+                const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
+                u64 x = tl[r];
+                if constexpr (POST) {
+                    if (a.post_scalar) x = gl_mul(x, a.post_scalar);
+                    if (a.post.lo) x = gl_mul(x, scale_factor_l(a.post, op + (u64)rows * r));
+                }
+                dst[r * ostride] = gl_canonw(x);
             }
-            dst[(u64)r * ostride] = gl_canonw(x);
+        } else {
+            const u64 ostride = rw;
+#pragma unroll 8
+            for (u32 it = 0; it < 32; it++) {
+                const u32 r = warp * kStageRowsPerWarp + it * kStageRowsPerIt + rsub;
+                u64 x = tl[r];
+                if constexpr (POST) {
+                    if (a.post_scalar) x = gl_mul(x, a.post_scalar);
+                    if (a.post.lo) x = gl_mul(x, scale_factor_l(a.post, op + (u64)rows * r));
+                }
+                dst[(u64)r * ostride] = gl_canonw(x);
+            }
         }
     }
 }
@@ -628,7 +646,7 @@ inline int get_tw_small(DeviceTables &t, int dev, unsigned log_b, unsigned log_n
 }
 
 template <typename K, typename A>
-inline int launch_fast_named(const char *name, K kernel, unsigned grid, const A &args, cudaStream_t st) {
+inline int launch_fast_named(const char *name, K kernel, dim3 grid, const A &args, cudaStream_t st) {
     TF21_LAUNCH_NAMED(name, kernel, grid, kFastThreads, kFastSmem, st, args);
     return 0;
 }
@@ -906,15 +924,15 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
             a.log_b = log_b;
             a.tw_scalar = tw_scalar;
             a.pre = cur_pre;
-            u64 grid = batch * n_outer * a.n_col_tiles;
-            if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+            if (batch > 65535 || n_outer > 65535 || inner_words > (1u << 21)) return TF21_E_LEN_TOO_LARGE;
+            const dim3 grid(a.n_col_tiles, n_outer, (unsigned)batch);
             const bool plain = cur_n_in == n && !cur_pre.lo && tw_full != nullptr;
             if (inverse) {
-                if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, true>), (unsigned)grid, a, st));
-                else TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, false>), (unsigned)grid, a, st));
+                if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, true>), grid, a, st));
+                else TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, false>), grid, a, st));
             } else {
-                if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, true>), (unsigned)grid, a, st));
-                else TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, false>), (unsigned)grid, a, st));
+                if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, true>), grid, a, st));
+                else TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, false>), grid, a, st));
             }
         } else {
             SmallColArgs a{};
@@ -955,17 +973,26 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     a.n1 = 1u << lead[0];
     a.n2 = n_lead > 1 ? 1u << lead[1] : 1u;
     a.n3 = n_lead > 2 ? 1u << lead[2] : 1u;
+    a.log_n1 = lead[0];
+    a.log_n2 = n_lead > 1 ? lead[1] : 0u;
     const u64 rows = n >> 10;
     a.n_cols_total = batch * rows * w;
     a.n_tiles = (rows * w) % kFastCols == 0 ? (u32)(rows * w / kFastCols) : 0u;
     a.t1 = t1;
     a.post_scalar = post_scalar;
     a.post = post;
-    u64 grid = (a.n_cols_total + kFastCols - 1) / kFastCols;
-    if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+    dim3 grid;
+    if (a.n_tiles && batch <= 65535) {
+        grid = dim3(a.n_tiles, (unsigned)batch);
+    } else {
+        a.n_tiles = 0;
+        const u64 g = (a.n_cols_total + kFastCols - 1) / kFastCols;
+        if (g > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+        grid = dim3((unsigned)g);
+    }
     const bool has_post = post_scalar != 0 || post.lo != nullptr;
 #define TF21_ROW_LAUNCH(I_, W_, P_) \
-    return launch_fast_named("ntt1024_row_kernel", (ntt1024_row_kernel<I_, W_, P_>), (unsigned)grid, a, st)
+    return launch_fast_named("ntt1024_row_kernel", (ntt1024_row_kernel<I_, W_, P_>), grid, a, st)
     if (w == 1) {
         if (inverse) { if (has_post) TF21_ROW_LAUNCH(true, 1, true); TF21_ROW_LAUNCH(true, 1, false); }
         if (has_post) TF21_ROW_LAUNCH(false, 1, true);
