@@ -73,8 +73,11 @@ __constant__ u64 c_tip5_rc_raw[TIP5_ROUNDS * TIP5_STATE];  // raw round constant
 #ifdef __CUDACC__
 
 // copy the 256-byte S-box table into shared memory (call once per CTA, then __syncthreads)
+// The table is computed, not copied: L[b] = ((b + 1)^3 + 256) mod 257 (tip5/mod.rs:1022-1053) is a handful of
+// integer instructions, whereas `c_tip5_lut[threadIdx.x]` is a lane-divergent constant-bank read that the
+// hardware serialises 32-fold (the kernel prologue showed up with 14 % of the stall samples in ncu).
 __device__ __forceinline__ void tip5_load_lut(uint8_t *s_lut) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = c_tip5_lut[i];
+    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = (uint8_t)(((i + 1) * (i + 1) * (i + 1) + 256u) % 257u);
 }
 
 __device__ __forceinline__ u32 tip5_lut_word(u32 w, const uint8_t *s_lut) {
