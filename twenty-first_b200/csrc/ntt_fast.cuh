@@ -8,20 +8,24 @@
 //     butterflies inside a 32-point DFT use power-of-two twiddles (omega_32 = 2^78 mod p, because
 //     omega_64 = 2^39, b_field_element.rs:43-78) -> shifts + Solinas folds, no 64x64 multiply;
 //   * the 32-point DFT is decimation in time on lazy values: the twiddled operand is made canonical
-//     (gl_shlc / gl_canonw), sums and differences stay "any u64" (gl_addl / gl_sub), so a butterfly
-//     is 8 ALU instructions + 1 IMAD.WIDE instead of 12 ALU instructions;
+//     (gl_shlc / gl_canonw), sums and differences stay "any u64" (gl_addl / gl_subl: two adds + a
+//     predicated two-add wrap correction), so a butterfly is 8 instructions + the twiddle;
 //   * one general multiply per element between the two steps (omega_1024^(b k1)) and, for column
 //     passes, one for the inter-pass twiddle omega_B^(i j_rest), read from a full [j_rest][i] table in
 //     L2 (coalesced, 8 MiB for B = 2^20).  Both steps run through the same loop body (halves the
 //     instruction footprint: the unrolled 32-point DFT is ~1400 instructions);
 //   * the 32 x 32 transpose between the steps goes through the warp's own slice of shared memory
-//     (__syncwarp only); __syncthreads is needed only around the coalesced global staging.
+//     (__syncwarp only); __syncthreads is needed only around the coalesced global staging;
+//   * the batched 2^20 transform takes template specialisations without index arithmetic or uniform
+//     branches in the staging loops (PLAIN column pass with cp.async staging, POST-less row pass),
+//     grids without index divisions and 32-bit row offsets.
 //
 // Values in flight are lazy (any u64 representative); only the last pass canonicalises on store, so
 // non-canonical input words are accepted as well.
 //
-// Shared-memory layout: tile[col][S] u64 with S = 1058 (= 2 mod 16: conflict-free for both the
-// 8-lanes-per-row staging pattern and the per-warp column patterns).
+// Shared-memory layout: tile[col][S] u64 with S = 1060 for 4 columns per CTA (= 4 mod 16: the 16 lanes of a
+// half warp -- 4 columns x 4 rows of the staging pattern -- hit 16 different 8-byte bank pairs; the per-warp
+// column patterns are unit-stride or stride 33).
 #pragma once
 #include "ntt_kernels.cuh"
 
@@ -41,10 +45,10 @@ namespace tf21 {
 #endif
 constexpr u32 kFastCols = TF21_FAST_COLS;  // word-columns (= warps) per CTA: 4, 8 or 16
 // u64 per column slice in shared memory (>= 32 * 33), chosen so that the staging pattern
-// (kFastCols lanes per row segment) is bank-conflict free: 2 S mod 32 = 64 / kFastCols
+// (kFastCols lanes per row segment) is bank-conflict free: S mod 16 = 16 / kFastCols
 constexpr u32 kFastS = kFastCols == 4 ? 1060 : kFastCols == 8 ? 1058 : 1057;
 constexpr u32 kFastThreads = kFastCols * 32;
-constexpr u32 kFastMinBlocks = 16 / kFastCols;  // 512 threads of 128 registers per SM
+constexpr u32 kFastMinBlocks = 16 / kFastCols;  // 512 threads of 128 registers per SM (the 32 x u64 column of a lane needs 64)
 constexpr u32 kStageRowsPerIt = 32 / kFastCols;  // rows covered by one warp instruction of the staging loops
 constexpr u32 kStageRowsPerWarp = 1024 / kFastCols;
 constexpr size_t kFastSmem = (size_t)kFastCols * kFastS * sizeof(u64);
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
     // 2^20-point blocks), so row offsets fit 32 bits: one narrow IMAD per row instead of a 64-bit multiply
     const u32 row_words = (u32)a.inner_words;
 
-    // ---- stage in: 8 lanes per 64-byte row segment, 4 rows per warp instruction ----
+    // ---- stage in: kFastCols lanes per row segment (32 bytes for 4 columns), 32 / kFastCols rows per warp instruction ----
     const u64 block_off = (u64)o * 1024 * a.inner_words + q0;
     {
         const u64 *src = a.src + (u64)b * a.src_array_words + block_off + c;
