@@ -667,3 +667,26 @@ def test_tip5_sample_indices_matches_oracle(tf, oracle):
         assert np.array_equal(got_state, want_state)
     with pytest.raises(tf.Tf21Error):
         tf.Tip5.sample_indices(rnd(1, 16), 12, 3)
+
+
+def test_ntt_batch_beyond_grid_y_limit(tf, oracle):
+    """more than 65535 arrays in one call: the row pass leaves its 2-D grid (arrays on blockIdx.y) for the
+    flat indexing; arrays are independent, so a sample of them is compared with the oracle"""
+    import torch
+
+    dev = importlib.import_module("twenty-first_b200.device")
+    log2n, batch = 12, 70000
+    n = 1 << log2n
+    x = torch.randint(0, 2**62, (batch * n,), dtype=torch.int64, device="cuda:0")
+    picks = [0, 1, 65534, 65535, 65536, batch - 1]
+    before = {b: x[b * n:(b + 1) * n].cpu().numpy().view(np.uint64).copy() for b in picks}
+    dev.ntt_(x, n, 1, False)
+    torch.cuda.synchronize()
+    for b in picks:
+        want = before[b].copy()
+        assert oracle.ntt(want, 1) == 0
+        assert np.array_equal(x[b * n:(b + 1) * n].cpu().numpy().view(np.uint64), want), b
+    dev.ntt_(x, n, 1, True)
+    torch.cuda.synchronize()
+    for b in picks:
+        assert np.array_equal(x[b * n:(b + 1) * n].cpu().numpy().view(np.uint64), before[b]), b
