@@ -34,6 +34,9 @@ namespace tf21 {
 #ifndef TF21_SHL_SINGLE
 #define TF21_SHL_SINGLE 1  /* shift form of the single-pass 2^10 kernel (no staging, lighter ALU load): the wide-multiply form is 4 % faster there */
 #endif
+#ifndef TF21_COL_MASKMUL
+#define TF21_COL_MASKMUL false  /* true: mask-style wrap corrections in the products of the column pass (it spilled with the predicated form before the PLAIN specialisation; now predicated is 2 % faster: 3.02 against 3.09 ms) */
+#endif
 #ifndef TF21_SHL_COL
 #define TF21_SHL_COL TF21_SHL_WIDE
 #endif
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
     const u32 qw = (u32)q0 + warp;  // < inner_words <= 2^21; w is 1 or 3: no run-time division
     const u64 jrest = a.w == 1 ? qw : qw / 3u;
     // inter-pass twiddle omega_B^(i * j_rest), i = lane + 32 k2: straight from the full table when there is one
-    dft1024_warp<INV, true, TF21_SHL_COL>(v, slice, a.t1 + lane,
+    dft1024_warp<INV, TF21_COL_MASKMUL, TF21_SHL_COL>(v, slice, a.t1 + lane,
                                           (PLAIN || a.tw_full) ? a.tw_full + jrest * 1024 + lane : nullptr, lane);
     if (!PLAIN && !a.tw_full) {
         const u64 bmask = (1ull << a.log_b) - 1;
