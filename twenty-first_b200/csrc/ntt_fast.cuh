@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
     const u32 qw = (u32)q0 + warp;  // < inner_words <= 2^21; w is 1 or 3: no run-time division
     const u64 jrest = a.w == 1 ? qw : qw / 3u;
     // inter-pass twiddle omega_B^(i * j_rest), i = lane + 32 k2: straight from the full table when there is one
-    dft1024_warp<INV, TF21_COL_MASKMUL, TF21_SHL_COL>(v, slice, a.t1 + lane,
+    dft1024_warp<INV, PLAIN ? TF21_COL_MASKMUL : true, TF21_SHL_COL>(v, slice, a.t1 + lane,
                                           (PLAIN || a.tw_full) ? a.tw_full + jrest * 1024 + lane : nullptr, lane);
     if (!PLAIN && !a.tw_full) {
         const u64 bmask = (1ull << a.log_b) - 1;
