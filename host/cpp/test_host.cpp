@@ -131,6 +131,9 @@ static void fast_multiply_and_square() {
     std::vector<BFieldElement> sq(199);
     oracle_poly_naive_multiply(words(a.coefficients.data()), 100, words(a.coefficients.data()), 100, 1, words(sq.data()));
     CHECK(a.fast_square().coefficients == sq);
+    // clean_divide: (a * b) / b == a  (polynomial.rs:2358-2413)
+    auto prod = a.fast_multiply(b);
+    CHECK(prod.clean_divide(b).coefficients == a.coefficients);
 }
 
 // tip5/mod.rs:1294-1325: hash_10 of zeros / hash_varlen snapshots, through the oracle that is pinned to them

@@ -182,6 +182,17 @@ struct Polynomial {
         check(tf21_poly_square(words(coefficients.data()), na, width_of<FF>(), words(p.coefficients.data())));
         return p;
     }
+    // polynomial.rs:2358-2413 (Polynomial<BFieldElement> only): exact quotient of a division without remainder
+    Polynomial clean_divide(const Polynomial &divisor) const {
+        static_assert(std::is_same<FF, BFieldElement>::value, "clean_divide is defined for Polynomial<BFieldElement>");
+        Polynomial q;
+        q.coefficients.resize(coefficients.size() ? coefficients.size() : 1);
+        uint64_t n_q = 0;
+        check(tf21_poly_clean_divide(words(coefficients.data()), coefficients.size(), words(divisor.coefficients.data()),
+                                     divisor.coefficients.size(), words(q.coefficients.data()), &n_q));
+        q.coefficients.resize(n_q);
+        return q;
+    }
     // polynomial.rs:2188-2331: result[(codeword, point)] flattened like the reference's flat_map
     static std::vector<FF> par_batch_coset_extrapolate(BFieldElement domain_offset, size_t codeword_length,
                                                        const std::vector<FF> &codewords,

@@ -16,6 +16,7 @@ pub const TF21_E_CUDA: c_int = -7;
 pub const TF21_E_BAD_ARG: c_int = -8;
 pub const TF21_E_LEAF_INDEX_INVALID: c_int = -9;
 pub const TF21_E_CAPACITY: c_int = -10;
+pub const TF21_E_DIVISION_BY_ZERO: c_int = -11;
 
 pub type tf21_stream_t = *mut c_void; // cudaStream_t
 
@@ -62,6 +63,7 @@ extern "C" {
                                             n_codewords: u64, width: u32, points: *const u64, n_points: u64,
                                             out: *mut u64, s: tf21_stream_t) -> c_int;
     pub fn tf21_tip5_sample_indices(state: *mut u64, upper_bound: u32, num_indices: u64, out: *mut u32) -> c_int;
+    pub fn tf21_poly_clean_divide(a: *const u64, n_a: u64, b: *const u64, n_b: u64, q_out: *mut u64, n_q: *mut u64) -> c_int;
     pub fn tf21_poly_square(a: *const u64, n_a: u64, width: u32, out: *mut u64) -> c_int;
     pub fn tf21_poly_square_dev(a: *const u64, n_a: u64, width: u32, out: *mut u64, s: tf21_stream_t) -> c_int;
 

@@ -44,6 +44,7 @@ enum {
     TF21_E_BAD_ARG = -8,         /* width not in {1,3}, NULL pointer with non-zero size, ...         */
     TF21_E_LEAF_INDEX_INVALID = -9, /* MerkleTreeError::LeafIndexInvalid, merkle_tree.rs:487-489       */
     TF21_E_CAPACITY = -10,       /* output buffer smaller than the result; *count holds the need     */
+    TF21_E_DIVISION_BY_ZERO = -11, /* polynomial.rs:556-559 `expect("divisor should be non-zero")` (panic) */
 };
 
 typedef void *tf21_stream_t; /* cudaStream_t */
@@ -123,6 +124,12 @@ int tf21_poly_mul_dev(const uint64_t *d_a, uint64_t n_a, const uint64_t *d_b, ui
 int tf21_poly_square(const uint64_t *a, uint64_t n_a, uint32_t width, uint64_t *out);
 int tf21_poly_square_dev(const uint64_t *d_a, uint64_t n_a, uint32_t width, uint64_t *d_out,
                          tf21_stream_t stream);
+
+/* Polynomial<BFieldElement>::clean_divide (polynomial.rs:2358-2413): q = a / b when the division leaves no
+ * remainder (the caller's promise, as in the reference; otherwise the result is unspecified).  Trailing zero
+ * coefficients are ignored; *n_q = deg a - deg b + 1 coefficients are written (0 if deg a < deg b).        */
+int tf21_poly_clean_divide(const uint64_t *a, uint64_t n_a, const uint64_t *b, uint64_t n_b,
+                           uint64_t *q_out, uint64_t *n_q);
 
 /* Polynomial::evaluate (polynomial.rs:309-319) of n_polys device-resident polynomials of n coefficients each
  * in n_points points (host array, same width as the coefficients): out[(poly * n_points + point) * width ..].  */

@@ -100,6 +100,8 @@ class Oracle:
         L.oracle_merkle_par_new.argtypes = [_u64p, u64, _u64p, i32, u64]
         L.oracle_merkle_sequential_frugal_root.argtypes = [_u64p, u64, _u64p]
         L.oracle_merkle_par_frugal_root.argtypes = [_u64p, u64, _u64p, i32, u64]
+        L.oracle_poly_naive_divide.argtypes = [_u64p, u64, _u64p, u64, _u64p, _u64p]
+        L.oracle_poly_naive_divide.restype = ctypes.c_int64
         L.oracle_poly_evaluate_w.argtypes = [_u64p, u64, u32, _u64p, _u64p]
         L.oracle_poly_evaluate_w.restype = None
         L.oracle_batch_coset_extrapolate.argtypes = [u64, u64, _u64p, u64, u32, _u64p, u64, _u64p]
@@ -270,6 +272,16 @@ class Oracle:
         root = np.zeros(5, dtype=np.uint64)
         rc = self.lib.oracle_merkle_par_frugal_root(_ptr(leafs if n else root), n, _ptr(root), threads, cutoff)
         return rc, root
+
+    def poly_naive_divide(self, a: np.ndarray, b: np.ndarray):
+        """(quotient, remainder) of Polynomial::naive_divide over BFieldElement; None for a zero divisor"""
+        quot = np.zeros(max(1, a.size), dtype=np.uint64)
+        rem = np.zeros(max(1, a.size), dtype=np.uint64)
+        k = self.lib.oracle_poly_naive_divide(_ptr(a if a.size else rem), a.size, _ptr(b if b.size else rem), b.size,
+                                              _ptr(quot), _ptr(rem))
+        if k < 0:
+            return None
+        return quot[:k].copy(), rem[: a.size].copy()
 
     def poly_evaluate_w(self, coeffs: np.ndarray, width: int, x: np.ndarray) -> np.ndarray:
         out = np.zeros(width, dtype=np.uint64)

@@ -796,3 +796,26 @@ void oracle_tip5_sample_indices(uint64_t state[16], uint32_t upper_bound, uint64
         if (bfe_value(element) != 0xFFFFFFFF00000000ull) out[produced++] = (uint32_t)bfe_value(element) % upper_bound;
     }
 }
+
+/* Polynomial::naive_divide, polynomial.rs:552-612 (BFieldElement): quotient (na - nb + 1 coefficients after
+ * trimming) and remainder by long division from the leading coefficient.  The checker of clean_divide
+ * (polynomial.rs:2358-2413), whose result is this quotient whenever the remainder is zero.
+ * Returns the number of quotient coefficients, -1 for a zero divisor.  rem needs na words. */
+int64_t oracle_poly_naive_divide(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint64_t *quot,
+                                 uint64_t *rem) {
+    while (na && a[na - 1] == 0) na--;
+    while (nb && b[nb - 1] == 0) nb--;
+    if (nb == 0) return -1;
+    memcpy(rem, a, na * sizeof(uint64_t));
+    if (na < nb) return 0;
+    uint64_t lc_inv = oracle_bfe_inverse_or_zero(b[nb - 1]);
+    uint64_t qd = na - nb;
+    for (uint64_t k = 0; k <= qd; k++) {
+        uint64_t top = na - 1 - k; /* current leading position of the remainder */
+        uint64_t qc = bfe_mul(rem[top], lc_inv);
+        quot[qd - k] = qc;
+        if (qc != 0)
+            for (uint64_t i = 0; i < nb; i++) rem[top - i] = bfe_sub(rem[top - i], bfe_mul(qc, b[nb - 1 - i]));
+    }
+    return (int64_t)(qd + 1);
+}

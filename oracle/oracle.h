@@ -36,6 +36,8 @@ void oracle_poly_naive_multiply(const uint64_t *a, uint64_t na, const uint64_t *
 int oracle_poly_fast_multiply(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint32_t w,
                               uint64_t *out);
 uint64_t oracle_poly_evaluate(const uint64_t *coeffs, uint64_t n_coeffs, uint64_t x_raw);
+int64_t oracle_poly_naive_divide(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint64_t *quot,
+                                 uint64_t *rem);
 void oracle_poly_evaluate_w(const uint64_t *coeffs, uint64_t n_coeffs, uint32_t w, const uint64_t *x, uint64_t *out);
 int oracle_batch_coset_extrapolate(uint64_t offset_raw, uint64_t n, const uint64_t *codewords, uint64_t n_codewords,
                                    uint32_t w, const uint64_t *points, uint64_t n_points, uint64_t *out);

@@ -690,3 +690,37 @@ def test_ntt_batch_beyond_grid_y_limit(tf, oracle):
     torch.cuda.synchronize()
     for b in picks:
         assert np.array_equal(x[b * n:(b + 1) * n].cpu().numpy().view(np.uint64), before[b]), b
+
+
+@pytest.mark.parametrize("nq,nb", [(1, 1), (1, 5), (7, 1), (33, 31), (600, 700), (1, 2000), (3000, 1100), (5000, 4000)])
+def test_poly_clean_divide_matches_long_division(tf, oracle, nq, nb):
+    """polynomial.rs:2358-2413: (q * b) / b == q, checked against the oracle's naive_divide (remainder zero)"""
+    q = rnd(0xD000 + nq, nq)
+    b = rnd(0xD100 + nb, nb)
+    q[-1] |= np.uint64(1)
+    b[-1] |= np.uint64(1)
+    a = oracle.poly_naive_multiply(q, b, 1)
+    want_q, rem = oracle.poly_naive_divide(a, b)
+    assert not rem.any() and np.array_equal(want_q, q)
+    got = tf.Polynomial(a).clean_divide(tf.Polynomial(b))
+    assert np.array_equal(got.coefficients, q)
+
+
+def test_poly_clean_divide_edge_cases(tf, oracle):
+    b = rnd(0xD200, 9)
+    # a root of the divisor on the first coset (offset 7): b = (x - 7) * c  ->  the offset is changed, result unchanged
+    c = rnd(0xD201, 20)
+    lin = np.array([oracle.bfe_new(P - 7), oracle.bfe_new(1)], dtype=np.uint64)
+    bb = oracle.poly_naive_multiply(lin, c, 1)
+    q = rnd(0xD202, 50)
+    a = oracle.poly_naive_multiply(q, bb, 1)
+    assert np.array_equal(tf.Polynomial(a).clean_divide(tf.Polynomial(bb)).coefficients, q)
+    # trailing zero coefficients are ignored; divisor with zero constant term (polynomial.rs:2372-2379)
+    xb = np.concatenate([np.zeros(1, dtype=np.uint64), b, np.zeros(3, dtype=np.uint64)])
+    a2 = oracle.poly_naive_multiply(q, xb[:10], 1)
+    assert np.array_equal(tf.Polynomial(np.concatenate([a2, np.zeros(5, dtype=np.uint64)])).clean_divide(
+        tf.Polynomial(xb)).coefficients, q)
+    # zero dividend, zero divisor
+    assert tf.Polynomial(np.zeros(4, dtype=np.uint64)).clean_divide(tf.Polynomial(b)).coefficients.size == 0
+    with pytest.raises(tf.Tf21Error):
+        tf.Polynomial(a).clean_divide(tf.Polynomial(np.zeros(3, dtype=np.uint64)))

@@ -110,6 +110,20 @@ class Polynomial:
                                     _ptr(out)))
         return Polynomial(out)
 
+    def clean_divide(self, divisor: "Polynomial") -> "Polynomial":
+        """polynomial.rs:2358-2413 (BFieldElement only): exact quotient of a division without remainder; panics
+        (raises) for a zero divisor"""
+        import ctypes
+
+        if self.width != 1 or divisor.width != 1:
+            raise TypeError("clean_divide is defined for Polynomial<BFieldElement>")
+        na, nb = self.coefficients.shape[0], divisor.coefficients.shape[0]
+        out = np.zeros(max(na, 1), dtype=np.uint64)
+        n_q = ctypes.c_uint64(0)
+        B.check(B.lib.tf21_poly_clean_divide(_ptr(self.coefficients), na, _ptr(divisor.coefficients), nb, _ptr(out),
+                                             ctypes.byref(n_q)))
+        return Polynomial(out[: n_q.value].copy())
+
     def fast_square(self) -> "Polynomial":
         """polynomial.rs:780-802; trailing zero coefficients are kept"""
         na = self.coefficients.shape[0]

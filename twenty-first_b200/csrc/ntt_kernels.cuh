@@ -317,6 +317,31 @@ __global__ void __launch_bounds__(kEvalThreads) poly_eval_kernel(const u64 *__re
     }
 }
 
+// ---- point-wise division for Polynomial::clean_divide (polynomial.rs:2358-2413) ---------------------------
+// q[i] = a[i] / b[i] on raw Montgomery words: raw(a / b) = a_raw * (b_raw)^-1 * 2^64 (plain mod-p arithmetic),
+// the inverse by Fermat (b^(p-2), p - 2 = 2^64 - 2^32 - 1).  A zero divisor value raises *flag (the coset hit a
+// root of the divisor; the host retries with another offset).  The result is lazy (any u64).
+__global__ void pointwise_divide_kernel(u64 *__restrict__ a, const u64 *__restrict__ b, u64 n, u32 *flag) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 x = gl_canon(b[i]);
+    if (x == 0) {
+        *flag = 1;
+        return;
+    }
+    // p - 2 = 0xFFFFFFFE_FFFFFFFF = (2^32 - 2) * 2^32 + (2^32 - 1):
+    //   f = x^(2^32 - 2) = (x^(2^31 - 1))^2,  x^(p-2) = f^(2^32) * (f * x)
+    u64 acc = x;  // x^(2^1 - 1)
+#pragma unroll 1
+    for (int k = 0; k < 30; k++) acc = gl_mul(gl_mul(acc, acc), x);  // x^(2^31 - 1)
+    const u64 f = gl_mul(acc, acc);
+    u64 hi = f;
+#pragma unroll 1
+    for (int k = 0; k < 32; k++) hi = gl_mul(hi, hi);
+    const u64 inv = gl_mul(hi, gl_mul(f, x));
+    a[i] = gl_mul(gl_mul(a[i], inv), GL_EPS);
+}
+
 // ---- host planning ------------------------------------------------------------------------------
 
 inline size_t col_pass_smem(u32 log_np) {

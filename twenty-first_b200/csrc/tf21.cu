@@ -159,6 +159,7 @@ const char *tf21_strerror(int code) {
         case TF21_E_BAD_ARG: return "bad argument";
         case TF21_E_LEAF_INDEX_INVALID: return "MerkleTreeError::LeafIndexInvalid";
         case TF21_E_CAPACITY: return "output buffer too small";
+        case TF21_E_DIVISION_BY_ZERO: return "divisor should be non-zero";
         default: return "unknown tf21 error";
     }
 }
@@ -517,6 +518,55 @@ int tf21_poly_mul(const uint64_t *a, uint64_t n_a, const uint64_t *b, uint64_t n
     TF21_TRY(tf21_poly_mul_dev(da.p, n_a, db.p, n_b, width, dout.p, nullptr));
     TF21_CUDA(cudaMemcpy(out, dout.p, len * width * sizeof(u64), cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// ---- Polynomial::clean_divide (next wave; polynomial.rs:2358-2413) ---------------------------
+// q = a / b for BFieldElement polynomials whose division leaves no remainder: both are evaluated on a coset of
+// order next_power_of_two(deg a + 1), divided point-wise and interpolated back.  The reference moves to the
+// extension field to dodge roots of the divisor on the coset; here the coset offset stays in the base field and
+// is changed when a root is hit (the quotient does not depend on it).
+int tf21_poly_clean_divide(const uint64_t *a, uint64_t n_a, const uint64_t *b, uint64_t n_b, uint64_t *q_out,
+                           uint64_t *n_q) {
+    if (!n_q || (n_a && !a) || (n_b && !b)) return TF21_E_BAD_ARG;
+    while (n_a && a[n_a - 1] == 0) n_a--;  // degree() ignores trailing zeros (polynomial.rs:181-191)
+    while (n_b && b[n_b - 1] == 0) n_b--;
+    if (n_b == 0) return TF21_E_DIVISION_BY_ZERO;  // "divisor should be non-zero"
+    if (n_a < n_b) {  // clean division of a lower-degree dividend: only the zero polynomial qualifies
+        *n_q = 0;
+        return 0;
+    }
+    const u64 len = n_a - n_b + 1;
+    *n_q = len;
+    if (!q_out) return TF21_E_BAD_ARG;
+    u64 order = 1;
+    while (order < n_a) order <<= 1;
+    TF21_TRY(check_ntt_len(order, 1));
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    DevBuf da, db, ea, eb, flag;
+    TF21_TRY(da.alloc(n_a));
+    TF21_TRY(db.alloc(n_b));
+    TF21_TRY(ea.alloc(order));
+    TF21_TRY(eb.alloc(order));
+    TF21_TRY(flag.alloc(1));
+    TF21_CUDA(cudaMemcpy(da.p, a, n_a * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_CUDA(cudaMemcpy(db.p, b, n_b * sizeof(u64), cudaMemcpyHostToDevice));
+    u64 offset = 7;  // BFieldElement::generator()
+    for (int attempt = 0; attempt < 8; attempt++, offset = hgl_mul(offset, 7)) {
+        const u64 offset_raw = hgl_to_raw(offset);
+        TF21_TRY(tf21_coset_evaluate_dev(da.p, n_a, 1, offset_raw, order, ea.p, nullptr));
+        TF21_TRY(tf21_coset_evaluate_dev(db.p, n_b, 1, offset_raw, order, eb.p, nullptr));
+        TF21_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(u64), nullptr));
+        TF21_LAUNCH(pointwise_divide_kernel, grid_for(order, 256), 256, 0, (cudaStream_t) nullptr, ea.p, eb.p, order,
+                    (u32 *)flag.p);
+        u64 hit = 0;
+        TF21_CUDA(cudaMemcpy(&hit, flag.p, sizeof(u64), cudaMemcpyDeviceToHost));
+        if (hit) continue;  // the coset contains a root of the divisor: next offset
+        TF21_TRY(tf21_coset_interpolate_dev(ea.p, order, 1, offset_raw, eb.p, nullptr));
+        TF21_CUDA(cudaMemcpy(q_out, eb.p, len * sizeof(u64), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    return TF21_E_BAD_ARG;
 }
 
 // ---- out-of-domain evaluation / coset extrapolation (next wave) ---------------------------
