@@ -63,6 +63,9 @@ extern "C" {
                                             n_codewords: u64, width: u32, points: *const u64, n_points: u64,
                                             out: *mut u64, s: tf21_stream_t) -> c_int;
     pub fn tf21_tip5_sample_indices(state: *mut u64, upper_bound: u32, num_indices: u64, out: *mut u32) -> c_int;
+    pub fn tf21_poly_reduce_by_ntt_friendly_modulus(coeffs: *const u64, n_coeffs: u64, width: u32, shift_ntt: *const u64,
+                                                    domain_length: u64, tail_length: u64, out: *mut u64,
+                                                    n_out: *mut u64) -> c_int;
     pub fn tf21_poly_clean_divide(a: *const u64, n_a: u64, b: *const u64, n_b: u64, q_out: *mut u64, n_q: *mut u64) -> c_int;
     pub fn tf21_poly_square(a: *const u64, n_a: u64, width: u32, out: *mut u64) -> c_int;
     pub fn tf21_poly_square_dev(a: *const u64, n_a: u64, width: u32, out: *mut u64, s: tf21_stream_t) -> c_int;

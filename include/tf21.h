@@ -125,6 +125,12 @@ int tf21_poly_square(const uint64_t *a, uint64_t n_a, uint32_t width, uint64_t *
 int tf21_poly_square_dev(const uint64_t *d_a, uint64_t n_a, uint32_t width, uint64_t *d_out,
                          tf21_stream_t stream);
 
+/* Polynomial::reduce_by_ntt_friendly_modulus (polynomial.rs:1087-1148): f mod (X^domain_length + shift(X)) with
+ * deg shift < tail_length and shift given as its NTT over domain_length points (shift_factor_ntt_with_tail_length,
+ * :1051-1074).  out receives min(n_coeffs, domain_length) elements; *n_out is set to that count.               */
+int tf21_poly_reduce_by_ntt_friendly_modulus(const uint64_t *coeffs, uint64_t n_coeffs, uint32_t width,
+                                             const uint64_t *shift_ntt, uint64_t domain_length,
+                                             uint64_t tail_length, uint64_t *out, uint64_t *n_out);
 /* Polynomial<BFieldElement>::clean_divide (polynomial.rs:2358-2413): q = a / b when the division leaves no
  * remainder (the caller's promise, as in the reference; otherwise the result is unspecified).  Trailing zero
  * coefficients are ignored; *n_q = deg a - deg b + 1 coefficients are written (0 if deg a < deg b).        */

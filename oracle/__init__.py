@@ -100,6 +100,8 @@ class Oracle:
         L.oracle_merkle_par_new.argtypes = [_u64p, u64, _u64p, i32, u64]
         L.oracle_merkle_sequential_frugal_root.argtypes = [_u64p, u64, _u64p]
         L.oracle_merkle_par_frugal_root.argtypes = [_u64p, u64, _u64p, i32, u64]
+        L.oracle_poly_reduce_by_ntt_friendly_modulus.argtypes = [_u64p, u64, u32, _u64p, u64, u64, _u64p]
+        L.oracle_poly_reduce_by_ntt_friendly_modulus.restype = ctypes.c_int64
         L.oracle_poly_naive_divide.argtypes = [_u64p, u64, _u64p, u64, _u64p, _u64p]
         L.oracle_poly_naive_divide.restype = ctypes.c_int64
         L.oracle_poly_evaluate_w.argtypes = [_u64p, u64, u32, _u64p, _u64p]
@@ -272,6 +274,14 @@ class Oracle:
         root = np.zeros(5, dtype=np.uint64)
         rc = self.lib.oracle_merkle_par_frugal_root(_ptr(leafs if n else root), n, _ptr(root), threads, cutoff)
         return rc, root
+
+    def poly_reduce_by_ntt_friendly_modulus(self, coeffs: np.ndarray, width: int, shift_ntt: np.ndarray, tail_length: int):
+        n, dl = coeffs.size // width, shift_ntt.size // width
+        out = np.zeros(max(1, max(n, dl) * width), dtype=np.uint64)
+        buf = coeffs if coeffs.size else np.zeros(width, dtype=np.uint64)
+        k = self.lib.oracle_poly_reduce_by_ntt_friendly_modulus(_ptr(buf), n, width, _ptr(shift_ntt), dl, tail_length,
+                                                                _ptr(out))
+        return k, out[: max(0, k) * width].copy()
 
     def poly_naive_divide(self, a: np.ndarray, b: np.ndarray):
         """(quotient, remainder) of Polynomial::naive_divide over BFieldElement; None for a zero divisor"""

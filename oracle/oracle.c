@@ -819,3 +819,40 @@ int64_t oracle_poly_naive_divide(const uint64_t *a, uint64_t na, const uint64_t 
     }
     return (int64_t)(qd + 1);
 }
+
+/* Polynomial::reduce_by_ntt_friendly_modulus, polynomial.rs:1087-1148, statement by statement (w = 1 or 3).
+ * out needs max(n, domain_length) elements; returns the number of elements of the result. */
+int64_t oracle_poly_reduce_by_ntt_friendly_modulus(const uint64_t *coeffs, uint64_t n, uint32_t w,
+                                                   const uint64_t *shift_ntt, uint64_t domain_length,
+                                                   uint64_t tail_length, uint64_t *out) {
+    if (domain_length == 0 || (domain_length & (domain_length - 1))) return ORACLE_E_LEN_NOT_POW2;
+    uint64_t chunk_size = domain_length - tail_length;
+    if (n < chunk_size + tail_length) { /* :1097-1099 */
+        memcpy(out, coeffs, n * w * sizeof(uint64_t));
+        return (int64_t)n;
+    }
+    uint64_t num_chunks = (n - (tail_length + chunk_size) + chunk_size - 1) / chunk_size;
+    uint64_t range_start = num_chunks * chunk_size;
+    uint64_t *window = (uint64_t *)calloc(domain_length * w, sizeof(uint64_t));
+    uint64_t *product = (uint64_t *)calloc(domain_length * w, sizeof(uint64_t));
+    uint64_t *next = (uint64_t *)calloc(domain_length * w, sizeof(uint64_t));
+    if (range_start < n) memcpy(window, coeffs + range_start * w, (n - range_start) * w * sizeof(uint64_t));
+    for (uint64_t ci = num_chunks; ci-- > 0;) {
+        memset(product, 0, domain_length * w * sizeof(uint64_t));
+        memcpy(product, window + tail_length * w, chunk_size * w * sizeof(uint64_t));
+        oracle_ntt(product, domain_length, w);
+        for (uint64_t i = 0; i < domain_length; i++) {
+            if (w == 1) product[i] = bfe_mul(product[i], shift_ntt[i]);
+            else { uint64_t t[3]; xfe_mul(product + 3 * i, shift_ntt + 3 * i, t); memcpy(product + 3 * i, t, sizeof(t)); }
+        }
+        oracle_intt(product, domain_length, w);
+        memset(next, 0, domain_length * w * sizeof(uint64_t));
+        memcpy(next + chunk_size * w, window, tail_length * w * sizeof(uint64_t));
+        memcpy(next, coeffs + ci * chunk_size * w, chunk_size * w * sizeof(uint64_t));
+        for (uint64_t i = 0; i < domain_length * w; i++) next[i] = bfe_sub(next[i], product[i]);
+        uint64_t *tmp = window; window = next; next = tmp;
+    }
+    memcpy(out, window, domain_length * w * sizeof(uint64_t));
+    free(window); free(product); free(next);
+    return (int64_t)domain_length;
+}

@@ -36,6 +36,9 @@ void oracle_poly_naive_multiply(const uint64_t *a, uint64_t na, const uint64_t *
 int oracle_poly_fast_multiply(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint32_t w,
                               uint64_t *out);
 uint64_t oracle_poly_evaluate(const uint64_t *coeffs, uint64_t n_coeffs, uint64_t x_raw);
+int64_t oracle_poly_reduce_by_ntt_friendly_modulus(const uint64_t *coeffs, uint64_t n, uint32_t w,
+                                                   const uint64_t *shift_ntt, uint64_t domain_length,
+                                                   uint64_t tail_length, uint64_t *out);
 int64_t oracle_poly_naive_divide(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint64_t *quot,
                                  uint64_t *rem);
 void oracle_poly_evaluate_w(const uint64_t *coeffs, uint64_t n_coeffs, uint32_t w, const uint64_t *x, uint64_t *out);

@@ -724,3 +724,28 @@ def test_poly_clean_divide_edge_cases(tf, oracle):
     assert tf.Polynomial(np.zeros(4, dtype=np.uint64)).clean_divide(tf.Polynomial(b)).coefficients.size == 0
     with pytest.raises(tf.Tf21Error):
         tf.Polynomial(a).clean_divide(tf.Polynomial(np.zeros(3, dtype=np.uint64)))
+
+
+@pytest.mark.parametrize("n,log_dl,tail,width", [(10, 4, 5, 1), (16, 4, 5, 1), (17, 4, 5, 1), (100, 4, 3, 3), (1000, 6, 20, 1),
+                                                 (5000, 8, 100, 3), (70000, 12, 1500, 1), (9, 3, 0, 1)])
+def test_poly_reduce_by_ntt_friendly_modulus_matches_oracle(tf, oracle, n, log_dl, tail, width):
+    """polynomial.rs:1087-1148, and its defining property: the result is f mod (X^dl + shift)"""
+    dl = 1 << log_dl
+    f = rnd(0xE000 + n, n * width)
+    shift = np.zeros(dl * width, dtype=np.uint64)
+    shift[: tail * width] = rnd(0xE100 + n, tail * width)   # deg shift < tail_length
+    shift_ntt = shift.copy()
+    assert oracle.ntt(shift_ntt, width) == 0
+    k, want = oracle.poly_reduce_by_ntt_friendly_modulus(f, width, shift_ntt, tail)
+    assert k == min(n, dl)
+    shp = (lambda a: a if width == 1 else a.reshape(-1, 3))
+    got = tf.Polynomial(shp(f)).reduce_by_ntt_friendly_modulus(shp(shift_ntt), tail)
+    assert np.array_equal(got.coefficients.reshape(-1), want)
+    if width == 1 and n >= dl:
+        # property: f - result is a multiple of the modulus M = X^dl + shift  ->  long division leaves remainder 0
+        modulus = np.concatenate([shift[:dl], np.array([oracle.bfe_new(1)], dtype=np.uint64)])
+        diff = f.copy()
+        for i in range(dl):
+            diff[i] = oracle.bfe_sub(int(diff[i]), int(want[i]))
+        _, rem = oracle.poly_naive_divide(diff, modulus)
+        assert not rem.any()

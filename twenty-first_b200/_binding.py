@@ -58,6 +58,7 @@ SIGNATURES = {
     "tf21_batch_coset_extrapolate": (i32, [u64, u64, vp, u64, u32, vp, u64, vp]),
     "tf21_batch_coset_extrapolate_dev": (i32, [u64, u64, vp, u64, u32, vp, u64, vp, vp]),
     "tf21_tip5_sample_indices": (i32, [vp, u32, u64, vp]),
+    "tf21_poly_reduce_by_ntt_friendly_modulus": (i32, [vp, u64, u32, vp, u64, u64, vp, ctypes.POINTER(u64)]),
     "tf21_poly_clean_divide": (i32, [vp, u64, vp, u64, vp, ctypes.POINTER(u64)]),
     "tf21_poly_square": (i32, [vp, u64, u32, vp]),
     "tf21_poly_square_dev": (i32, [vp, u64, u32, vp, vp]),

@@ -110,6 +110,19 @@ class Polynomial:
                                     _ptr(out)))
         return Polynomial(out)
 
+    def reduce_by_ntt_friendly_modulus(self, shift_ntt: np.ndarray, tail_length: int) -> "Polynomial":
+        """polynomial.rs:1087-1148; panics (raises) unless len(shift_ntt) is a power of two"""
+        import ctypes
+
+        shift_ntt = _words(np.ascontiguousarray(shift_ntt))
+        n, dl = self.coefficients.shape[0], shift_ntt.shape[0]
+        m = min(n, dl)
+        out = np.zeros((max(m, 1),) if self.width == 1 else (max(m, 1), 3), dtype=np.uint64)
+        n_out = ctypes.c_uint64(0)
+        B.check(B.lib.tf21_poly_reduce_by_ntt_friendly_modulus(_ptr(self.coefficients), n, self.width, _ptr(shift_ntt), dl,
+                                                               tail_length, _ptr(out), ctypes.byref(n_out)))
+        return Polynomial(out[: n_out.value].copy())
+
     def clean_divide(self, divisor: "Polynomial") -> "Polynomial":
         """polynomial.rs:2358-2413 (BFieldElement only): exact quotient of a division without remainder; panics
         (raises) for a zero divisor"""

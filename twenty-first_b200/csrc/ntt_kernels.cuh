@@ -317,6 +317,18 @@ __global__ void __launch_bounds__(kEvalThreads) poly_eval_kernel(const u64 *__re
     }
 }
 
+// ---- window update of Polynomial::reduce_by_ntt_friendly_modulus (polynomial.rs:1126-1143) ---------------
+// new[i] = (i < chunk ? coeffs[chunk_index * chunk + i] : old[i - chunk]) - product[i], element-wise on
+// w-word elements; `old` holds the low tail_length elements of the previous window.  Canonical output.
+__global__ void reduce_window_kernel(const u64 *__restrict__ coeffs_chunk, const u64 *__restrict__ old_tail,
+                                     const u64 *__restrict__ product, u64 chunk_words, u64 total_words,
+                                     u64 *__restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_words) return;
+    const u64 x = i < chunk_words ? coeffs_chunk[i] : old_tail[i - chunk_words];
+    out[i] = gl_sub(gl_canon(x), gl_canon(product[i]));
+}
+
 // ---- point-wise division for Polynomial::clean_divide (polynomial.rs:2358-2413) ---------------------------
 // q[i] = a[i] / b[i] on raw Montgomery words: raw(a / b) = a_raw * (b_raw)^-1 * 2^64 (plain mod-p arithmetic),
 // the inverse by Fermat (b^(p-2), p - 2 = 2^64 - 2^32 - 1).  A zero divisor value raises *flag (the coset hit a

@@ -2,6 +2,7 @@
 // staging, and dispatch into the sm_100a kernels.  Single translation unit (the kernels live in the
 // included .cuh files) so the __constant__ tables are shared without relocatable device code.
 #include <algorithm>
+#include <cstring>
 #include "ntt_fast.cuh"
 #include "tip5_kernels.cuh"
 
@@ -517,6 +518,67 @@ int tf21_poly_mul(const uint64_t *a, uint64_t n_a, const uint64_t *b, uint64_t n
     TF21_CUDA(cudaMemcpy(db.p, b, n_b * width * sizeof(u64), cudaMemcpyHostToDevice));
     TF21_TRY(tf21_poly_mul_dev(da.p, n_a, db.p, n_b, width, dout.p, nullptr));
     TF21_CUDA(cudaMemcpy(out, dout.p, len * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- Polynomial::reduce_by_ntt_friendly_modulus (next wave; polynomial.rs:1087-1148) --------
+// f mod (X^(chunk + tail) + shift(X)), deg shift < tail, with shift given in the NTT domain (domain_length =
+// chunk + tail values).  The chunk loop of the reference stays (each step needs the window of the previous one),
+// every step is device work: zero-extended NTT of the top of the window, Hadamard product with shift_ntt,
+// inverse NTT, window update.
+int tf21_poly_reduce_by_ntt_friendly_modulus(const uint64_t *coeffs, uint64_t n_coeffs, uint32_t width,
+                                             const uint64_t *shift_ntt, uint64_t domain_length,
+                                             uint64_t tail_length, uint64_t *out, uint64_t *n_out) {
+    if (width != 1 && width != 3) return TF21_E_BAD_ARG;
+    if (domain_length == 0 || (domain_length & (domain_length - 1))) return TF21_E_LEN_NOT_POW2;  // :1094 assert
+    TF21_TRY(check_ntt_len(domain_length, width));
+    if (!n_out || tail_length >= domain_length || !shift_ntt || (n_coeffs && (!coeffs || !out))) return TF21_E_BAD_ARG;
+    const u64 chunk = domain_length - tail_length, w = width;
+    if (n_coeffs < domain_length) {  // :1097-1099: nothing to reduce
+        if (n_coeffs) std::memcpy(out, coeffs, n_coeffs * w * sizeof(u64));
+        *n_out = n_coeffs;
+        return 0;
+    }
+    *n_out = domain_length;
+    const u64 n_chunks = (n_coeffs - domain_length + chunk - 1) / chunk;  // :1100-1101
+    const u64 range_start = n_chunks * chunk;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    cudaStream_t st = nullptr;
+    DevBuf dc, dshift, win[2], prod;
+    TF21_TRY(dc.alloc(n_coeffs * w));
+    TF21_TRY(dshift.alloc(domain_length * w));
+    TF21_TRY(win[0].alloc(domain_length * w));
+    TF21_TRY(win[1].alloc(domain_length * w));
+    TF21_TRY(prod.alloc(domain_length * w));
+    TF21_CUDA(cudaMemcpy(dc.p, coeffs, n_coeffs * w * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_CUDA(cudaMemcpy(dshift.p, shift_ntt, domain_length * w * sizeof(u64), cudaMemcpyHostToDevice));
+    // working_window = coefficients[range_start..] zero-padded to chunk + tail (:1103-1109)
+    TF21_CUDA(cudaMemsetAsync(win[0].p, 0, domain_length * w * sizeof(u64), st));
+    if (range_start < n_coeffs)
+        TF21_CUDA(cudaMemcpyAsync(win[0].p, dc.p + range_start * w, (n_coeffs - range_start) * w * sizeof(u64),
+                                  cudaMemcpyDeviceToDevice, st));
+    const u64 rinv = hgl_inv(GL_EPS);
+    const u64 post_scalar = hgl_inv(domain_length % GL_P);
+    int cur = 0;
+    for (u64 ci = n_chunks; ci-- > 0;) {
+        // product = iNTT( NTT( window[tail..] | 0 x tail ) .* shift_ntt )   (:1112-1124)
+        if (domain_length > 1) {
+            TF21_TRY(ntt_run_locked(*t, win[cur].p + tail_length * w, chunk, prod.p, domain_length, width, 1, 0, NO_SCALE,
+                                    NO_SCALE, 0, st));
+        } else {
+            TF21_CUDA(cudaMemcpyAsync(prod.p, win[cur].p + tail_length * w, w * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        }
+        TF21_LAUNCH(hadamard_kernel, grid_for(domain_length, 256), 256, 0, st, prod.p, dshift.p, domain_length, width, rinv);
+        if (domain_length > 1)
+            TF21_TRY(ntt_run_locked(*t, prod.p, domain_length, prod.p, domain_length, width, 1, 1, NO_SCALE, NO_SCALE,
+                                    post_scalar, st));
+        // window = [coefficients of chunk ci | old window[0..tail)] - product   (:1126-1143)
+        TF21_LAUNCH(reduce_window_kernel, grid_for(domain_length * w, 256), 256, 0, st, dc.p + ci * chunk * w, win[cur].p,
+                    prod.p, chunk * w, domain_length * w, win[cur ^ 1].p);
+        cur ^= 1;
+    }
+    TF21_CUDA(cudaMemcpy(out, win[cur].p, domain_length * w * sizeof(u64), cudaMemcpyDeviceToHost));
     return 0;
 }
 
