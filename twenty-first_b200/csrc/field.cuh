@@ -33,6 +33,12 @@ typedef uint32_t u32;
 #define TF21_SUB_WIDE 0  /* measured -3 %: the FMA pipe is as loaded as the ALU pipe */
 #endif
 
+#ifndef TF21_SHL_CARRY
+#define TF21_SHL_CARRY 1  /* carry-form canonicalisation in the q == 0 fold and z0 * EPS on the ALU in the q == 2 fold: 2^20 batch 2.97 -> 2.92 ms */
+#endif
+#ifndef TF21_CANON_CARRY
+#define TF21_CANON_CARRY 1  /* carry form of the canonicalisation: one ALU instruction less per use, 2^20 batch 3.02 -> 2.96 ms */
+#endif
 #ifndef TF21_MUL_WIDE_LOW
 #define TF21_MUL_WIDE_LOW 1
 #endif
@@ -456,7 +462,28 @@ __device__ __forceinline__ u64 gl_subp(u64 a, u64 t) {  // a any, t <= p -> any;
         : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)t), "r"((u32)(t >> 32)));
     return s;
 }
+// carry form: x >= p  <=>  x + EPS carries out of 64 bits; then x - p = (x + EPS) mod 2^64.  Two adds with carry
+// + a predicated 64-bit move instead of two compares + two predicated adds (one ALU instruction less).
+__device__ __forceinline__ u64 gl_canonc(u64 x) {
+    u64 s;
+    asm("{\n\t.reg .u32 c; .reg .pred p; .reg .u64 v, w;\n\t"
+        "add.cc.u64 w,%1,0xffffffff;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.eq.u32 p,c,0;\n\t"
+        "mov.b64 v,%1;\n\t"
+        "@p bra GLCC%=;\n\t"
+        "mov.b64 v,w;\n\t"
+        "GLCC%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(s)
+        : "l"(x));
+    return s;
+}
 __device__ __forceinline__ u64 gl_canonp(u64 x) {  // any -> [0, p)
+#if TF21_CANON_CARRY
+    return gl_canonc(x);
+#endif
     u64 s;
     asm("{\n\t.reg .u32 lo,hi; .reg .pred p1,p2; .reg .u64 v;\n\t"
         "mov.b64 {lo,hi},%1;\n\t"
@@ -559,7 +586,26 @@ __device__ __forceinline__ u64 gl_shlc(u64 x) {
         asm("mad.lo.cc.u32 %0,%5,0xffffffff,%3;\n\tmadc.hi.cc.u32 %1,%5,0xffffffff,%4;\n\taddc.u32 %2,0,0;"
             : "=r"(lo), "=r"(hi), "=r"(c)
             : "r"(z0), "r"(z1), "r"(z2));
-#if TF21_PRED_FIX
+#if TF21_SHL_CARRY
+        // carry form: with s = (hi:lo) and c the carry of the fold, the result is s + EPS (mod 2^64) when c is set
+        // (s < 2^63, no second carry) or when s + EPS carries (s >= p), else s: two adds, one predicate OR, a
+        // predicated move -- two compares less than the form below
+        u64 r;
+        asm("{\n\t.reg .pred p1,p2; .reg .u32 k; .reg .u64 v,w;\n\t"
+            "mov.b64 v,{%1,%2};\n\t"
+            "add.cc.u64 w,v,0xffffffff;\n\t"
+            "addc.u32 k,0,0;\n\t"
+            "setp.ne.u32 p1,k,0;\n\t"
+            "setp.ne.or.u32 p2,%3,0,p1;\n\t"
+            "@!p2 bra GLQC%=;\n\t"
+            "mov.b64 v,w;\n\t"
+            "GLQC%=:\n\t"
+            "mov.b64 %0,v;\n\t"
+            "}"
+            : "=l"(r)
+            : "r"(lo), "r"(hi), "r"(c));
+        return r;
+#elif TF21_PRED_FIX
         u64 r;
         asm("{\n\t.reg .pred p1,p2,p3; .reg .u64 v;\n\t"
             "mov.b64 v,{%1,%2};\n\t"
@@ -587,7 +633,14 @@ __device__ __forceinline__ u64 gl_shlc(u64 x) {
         return gl_subl(T1, T2);
     } else {
         // z * 2^64 = z0 * EPS - (z2:z1):  z0 * EPS <= (2^32-1)^2 < p, (z2:z1) < 2^63
+#if TF21_SHL_CARRY
+        // z0 * EPS = (z0 << 32) - z0 as a 64-bit difference on the ALU instead of a wide multiply
+        u32 alo, ahi;
+        asm("sub.cc.u32 %0,0,%2;\n\tsubc.u32 %1,%2,0;" : "=r"(alo), "=r"(ahi) : "r"(z0));
+        const u64 a = gl_pack(alo, ahi);
+#else
         const u64 a = (u64)z0 * GL_EPS;
+#endif
         return gl_subl(a, gl_pack(z1, z2));
     }
 }
