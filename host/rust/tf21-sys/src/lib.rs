@@ -89,6 +89,8 @@ extern "C" {
     pub fn tf21_merkle_scatter_subtree_dev(local_nodes: *const u64, n_local_leafs: u64, shard: u64, n_shards: u64,
                                            global_nodes: *mut u64, s: tf21_stream_t) -> c_int;
 
+    pub fn tf21_ntt_sharded(data: *mut u64, n: u64, width: u32, batch: u64, inverse: c_int, n_shards: u32) -> c_int;
+    pub fn tf21_merkle_build_sharded(leafs: *const u64, n_leafs: u64, nodes_out: *mut u64, n_shards: u32) -> c_int;
     pub fn tf21_merkle_auth_structure_node_indices(n_leafs: u64, leaf_indices: *const u64, n_indices: u64,
                                                    out: *mut u64, capacity: u64, count: *mut u64) -> c_int;
     pub fn tf21_merkle_authentication_structure_dev(nodes: *const u64, n_leafs: u64, leaf_indices: *const u64,

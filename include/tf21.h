@@ -194,6 +194,15 @@ int tf21_merkle_scatter_subtree_dev(const uint64_t *d_local_nodes, uint64_t n_lo
                                     uint64_t shard, uint64_t n_shards, uint64_t *d_global_nodes,
                                     tf21_stream_t stream);
 
+/* ---- single-process sharding over the visible devices ---------------------------- */
+/* `batch` columns split over n_shards host threads, shard s on device s % (visible devices); no exchange.  */
+int tf21_ntt_sharded(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch, int inverse,
+                     uint32_t n_shards);
+/* n_shards (a power of two) subtrees built independently, then the top log2(n_shards) levels from the shard
+ * roots (the tree cap); nodes_out as tf21_merkle_build.                                                    */
+int tf21_merkle_build_sharded(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out,
+                              uint32_t n_shards);
+
 /* ---- next wave: authentication structures (merkle_tree.rs:449-542, 614-622) ---- */
 /* MerkleTree::authentication_structure_node_indices: node indices needed to prove the given leaf
  * indices, descending, de-duplicated.  Pure host logic (no device).  *count is always set to the number

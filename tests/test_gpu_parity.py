@@ -749,3 +749,27 @@ def test_poly_reduce_by_ntt_friendly_modulus_matches_oracle(tf, oracle, n, log_d
             diff[i] = oracle.bfe_sub(int(diff[i]), int(want[i]))
         _, rem = oracle.poly_naive_divide(diff, modulus)
         assert not rem.any()
+
+
+@pytest.mark.parametrize("n_shards", [1, 2, 4, 8])
+def test_single_process_sharded_entry_points(tf, oracle, n_shards):
+    """columns / subtrees split over host threads (shard s on device s % visible devices, so the
+    index algebra is exercised on one GPU as well); results equal the unsharded ones"""
+    log2n, batch = 12, 11
+    x = rnd(0xF000 + n_shards, batch << log2n)
+    want = x.copy()
+    assert oracle.ntt_batch(want, 1 << log2n, 1, batch, False) == 0
+    got = x.copy()
+    tf.check(tf.lib.tf21_ntt_sharded(got.ctypes.data, 1 << log2n, 1, batch, 0, n_shards))
+    assert np.array_equal(got, want)
+    tf.check(tf.lib.tf21_ntt_sharded(got.ctypes.data, 1 << log2n, 1, batch, 1, n_shards))
+    assert np.array_equal(got, x)
+    for height in (0, 2, 3, 11):
+        n = 1 << height
+        leafs = rnd(0xF100 + height, 5 * n)
+        rc, want_nodes = oracle.merkle_par_new(leafs)
+        assert rc == 0
+        nodes = np.zeros(10 * n, dtype=np.uint64)
+        tf.check(tf.lib.tf21_merkle_build_sharded(leafs.ctypes.data, n, nodes.ctypes.data, n_shards))
+        assert np.array_equal(nodes, want_nodes), (height, n_shards)
+    assert tf.lib.tf21_merkle_build_sharded(leafs.ctypes.data, n, nodes.ctypes.data, 3) == tf.E_BAD_ARG

@@ -76,6 +76,8 @@ SIGNATURES = {
     "tf21_merkle_build_dev": (i32, [vp, u64, vp, vp]),
     "tf21_merkle_root_dev": (i32, [vp, u64, vp, vp]),
     "tf21_merkle_scatter_subtree_dev": (i32, [vp, u64, u64, u64, vp, vp]),
+    "tf21_ntt_sharded": (i32, [vp, u64, u32, u64, i32, u32]),
+    "tf21_merkle_build_sharded": (i32, [vp, u64, vp, u32]),
     "tf21_merkle_auth_structure_node_indices": (i32, [u64, vp, u64, vp, u64, ctypes.POINTER(u64)]),
     "tf21_merkle_authentication_structure_dev": (i32, [vp, u64, vp, u64, vp, u64, ctypes.POINTER(u64), vp]),
     "tf21_merkle_authentication_structure_from_leafs": (i32, [vp, u64, vp, u64, vp, u64, ctypes.POINTER(u64)]),

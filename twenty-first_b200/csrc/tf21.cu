@@ -2,6 +2,7 @@
 // staging, and dispatch into the sm_100a kernels.  Single translation unit (the kernels live in the
 // included .cuh files) so the __constant__ tables are shared without relocatable device code.
 #include <algorithm>
+#include <thread>
 #include <cstring>
 #include "ntt_fast.cuh"
 #include "tip5_kernels.cuh"
@@ -981,6 +982,85 @@ int tf21_mmr_bag_peaks(const uint64_t *peaks, uint64_t n_peaks, uint64_t leaf_co
     if (n_peaks) TF21_CUDA(cudaMemcpy(bp.p, peaks, 5 * n_peaks * sizeof(u64), cudaMemcpyHostToDevice));
     TF21_TRY(tf21_mmr_bag_peaks_dev(bp.p, n_peaks, leaf_count, bo.p, nullptr));
     TF21_CUDA(cudaMemcpy(out, bo.p, 5 * sizeof(u64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- single-process sharding over the visible devices -------------------------------
+// Columns and Merkle subtrees are independent (the reference's rayon split, ntt.rs:250-269 /
+// merkle_tree.rs:165-212, 247-275), so one host thread per shard drives its own device; there is no data-path
+// exchange: the only cross-shard step is finishing the top log2(n_shards) levels from the shard roots.
+// Shard s runs on device s % n_devices, so the index algebra is testable on a single GPU.
+static int visible_devices(int *n) {
+    TF21_CUDA(cudaGetDeviceCount(n));
+    return *n > 0 ? 0 : TF21_E_CUDA;
+}
+
+int tf21_ntt_sharded(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch, int inverse, uint32_t n_shards) {
+    TF21_TRY(check_ntt_len(n, width));
+    if (n <= 1 || batch == 0) return 0;
+    if (!data || n_shards == 0) return TF21_E_BAD_ARG;
+    int n_dev = 0, prev = 0;
+    TF21_TRY(visible_devices(&n_dev));
+    cudaGetDevice(&prev);
+    if (n_shards > batch) n_shards = (uint32_t)batch;
+    std::vector<int> rc(n_shards, 0);
+    std::vector<std::thread> workers;
+    const u64 per = batch / n_shards, extra = batch % n_shards;
+    u64 first = 0;
+    for (uint32_t sh = 0; sh < n_shards; sh++) {
+        const u64 cnt = per + (sh < extra ? 1 : 0);
+        u64 *slice = data + first * n * width;
+        first += cnt;
+        workers.emplace_back([=, &rc] {
+            if (cudaSetDevice((int)(sh % n_dev)) != cudaSuccess) {
+                rc[sh] = TF21_E_CUDA;
+                return;
+            }
+            rc[sh] = inverse ? tf21_intt(slice, n, width, cnt) : tf21_ntt(slice, n, width, cnt);
+        });
+    }
+    for (auto &w : workers) w.join();
+    cudaSetDevice(prev);
+    for (int r : rc)
+        if (r) return r;
+    return 0;
+}
+
+int tf21_merkle_build_sharded(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out, uint32_t n_shards) {
+    TF21_TRY(check_leaf_count(n_leafs));
+    if (!leafs || !nodes_out) return TF21_E_BAD_ARG;
+    if (n_shards == 0 || (n_shards & (n_shards - 1))) return TF21_E_BAD_ARG;  // subtrees are powers of two
+    while (n_shards > 1 && n_leafs / n_shards < 1) n_shards >>= 1;
+    if (n_shards == 1) return tf21_merkle_build(leafs, n_leafs, nodes_out);
+    int n_dev = 0, prev = 0;
+    TF21_TRY(visible_devices(&n_dev));
+    cudaGetDevice(&prev);
+    const u64 local = n_leafs / n_shards;
+    std::vector<int> rc(n_shards, 0);
+    std::vector<std::vector<u64>> trees(n_shards);
+    std::vector<std::thread> workers;
+    for (uint32_t sh = 0; sh < n_shards; sh++) {
+        workers.emplace_back([=, &rc, &trees] {
+            if (cudaSetDevice((int)(sh % n_dev)) != cudaSuccess) {
+                rc[sh] = TF21_E_CUDA;
+                return;
+            }
+            trees[sh].resize(10 * local);
+            rc[sh] = tf21_merkle_build(leafs + 5 * sh * local, local, trees[sh].data());
+        });
+    }
+    for (auto &w : workers) w.join();
+    cudaSetDevice(prev);
+    for (int r : rc)
+        if (r) return r;
+    // local node j of shard sh (level width wd = 2^floor(log2 j)) sits at global n_shards * wd + sh * wd + (j - wd)
+    for (uint32_t sh = 0; sh < n_shards; sh++)
+        for (u64 wd = 1; wd <= local; wd <<= 1)
+            std::memcpy(nodes_out + 5 * (n_shards * wd + sh * wd), trees[sh].data() + 5 * wd, 5 * wd * sizeof(u64));
+    // the cap: nodes[n_shards .. 2 n_shards) are the shard roots; finish nodes[1 .. n_shards) from them
+    std::vector<u64> cap(10 * n_shards);
+    TF21_TRY(tf21_merkle_build(nodes_out + 5 * n_shards, n_shards, cap.data()));
+    std::memcpy(nodes_out, cap.data(), 5 * n_shards * sizeof(u64));  // includes nodes[0] = 0
     return 0;
 }
 
