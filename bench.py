@@ -179,8 +179,10 @@ def main():
             "impl": "reference", "metric": METRIC, "value": r["ntt_per_s"], "unit": "NTT/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"batched 2^{LOG2N}-point BFieldElement NTT+iNTT, reference algorithm on host cores",
-                       "sample": r["sample"]},
+            # same workload as the GPU arm (BASELINE configs[1]); each step is a bounded sample of it
+            "config": {"workload": f"batched {args.cols}x2^{LOG2N}-point BFieldElement NTT then iNTT per GPU (BASELINE configs[1]), "
+                                   "reference algorithm (CPU port) on all host threads",
+                       "columns_per_gpu": args.cols, "log2_n": LOG2N, "sample": r["sample"]},
             "cpu_baseline": {"value": r["ntt_per_s"], "unit": "NTT/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"], "merkle_leaves_per_s": r["merkle_leaves_per_s"]},
             "e2e": {"value": r["ntt_per_s"], "unit": "NTT/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
