@@ -34,6 +34,12 @@ namespace tf21 {
 #ifndef TF21_SHL_SINGLE
 #define TF21_SHL_SINGLE 1  /* shift form of the single-pass 2^10 kernel (no staging, lighter ALU load): the wide-multiply form is 4 % faster there */
 #endif
+#ifndef TF21_ROW_STORE128
+#define TF21_ROW_STORE128 1  /* 16-byte stores of column pairs in the stage-out loops: 2.92 -> 2.90 ms */
+#endif
+#ifndef TF21_COL_STORE128
+#define TF21_COL_STORE128 0
+#endif
 #ifndef TF21_COL_MASKMUL
 #define TF21_COL_MASKMUL false  /* true: mask-style wrap corrections in the products of the column pass (it spilled with the predicated form before the PLAIN specialisation; now predicated is 2 % faster: 3.02 against 3.09 ms) */
 #endif
@@ -248,6 +254,20 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
     __syncthreads();
 
     // ---- stage out (lazy values: the next pass accepts any representative) ----
+#if TF21_COL_STORE128
+    if (kFastCols == 4) {  // two adjacent word-columns per lane: one 16-byte store per row
+        const u32 cp = lane & 1, rs = lane >> 1;
+        const u64 *t0 = tile + (2 * cp) * kFastS, *t1c = t0 + kFastS;
+        ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(a.dst + (u64)b * a.dst_array_words + block_off + 2 * cp);
+        const u32 row2 = row_words >> 1;  // inner_words = 1024 w: even
+#pragma unroll 8
+        for (u32 it = 0; it < 16; it++) {
+            const u32 r = warp * kStageRowsPerWarp + it * 16 + rs;
+            d2[r * row2] = make_ulonglong2(t0[r], t1c[r]);
+        }
+        return;
+    }
+#endif
     {
         u64 *dst = a.dst + (u64)b * a.dst_array_words + block_off + c;
         const u64 *tl = tile + c * kFastS;
@@ -323,6 +343,21 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kern
         u64 *dst = a.dst + b * a.array_words + tc;
         const u64 *tl = tile + c8 * kFastS;
         const u32 op = tc / W;  // element index = op + rows * r
+#if TF21_ROW_STORE128
+        if (tiled && !POST && kFastCols == 4 && (rw & 1) == 0 && a.array_words < (1ull << 29)) {
+            // two adjacent word-columns per lane: one 16-byte store per row pair instead of two 8-byte stores
+            const u32 cp = lane & 1, rs = lane >> 1;  // 16 rows per warp instruction
+            const u64 *t0 = tile + (2 * cp) * kFastS, *t1c = t0 + kFastS;
+            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(a.dst + b_cta * a.array_words + tc_cta + 2 * cp);
+            const u32 ostride2 = rw >> 1;
+#pragma unroll 8
+            for (u32 it = 0; it < 16; it++) {
+                const u32 r = warp * kStageRowsPerWarp + it * 16 + rs;
+                d2[r * ostride2] = make_ulonglong2(gl_canonw(t0[r]), gl_canonw(t1c[r]));
+            }
+            return;
+        }
+#endif
         if (a.array_words < (1ull << 29)) {
             // byte offsets of an array below 4 GiB: 32-bit row offsets (one narrow IMAD per row)
             const u32 ostride = rw;
