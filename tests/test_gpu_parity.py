@@ -773,3 +773,32 @@ def test_single_process_sharded_entry_points(tf, oracle, n_shards):
         tf.check(tf.lib.tf21_merkle_build_sharded(leafs.ctypes.data, n, nodes.ctypes.data, n_shards))
         assert np.array_equal(nodes, want_nodes), (height, n_shards)
     assert tf.lib.tf21_merkle_build_sharded(leafs.ctypes.data, n, nodes.ctypes.data, 3) == tf.E_BAD_ARG
+
+
+def test_device_entry_points_on_a_non_default_stream(tf, oracle):
+    """the *_dev entry points are stream ordered: run them on a side stream (with work queued on the default
+    stream meanwhile) and compare with the oracle"""
+    import torch
+
+    dev = importlib.import_module("twenty-first_b200.device")
+    side = torch.cuda.Stream()
+    n, batch = 1 << 20, 3
+    x = rnd(0x5EED, n * batch)
+    want = x.copy()
+    assert oracle.ntt_batch(want, n, 1, batch, False) == 0
+    leafs = rnd(0x5EEE, 5 << 12)
+    rc, want_nodes = oracle.merkle_par_new(leafs)
+    assert rc == 0
+    d_x = torch.from_numpy(x.view(np.int64)).cuda()
+    d_leafs = torch.from_numpy(leafs.view(np.int64)).cuda()
+    d_nodes = torch.zeros(10 << 12, dtype=torch.int64, device="cuda")
+    noise = torch.randint(0, 2**62, (64 << 20,), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        dev.ntt_(d_x, n, 1, False)
+        dev.merkle_build(d_leafs, d_nodes)
+    dev.ntt_(noise, n, 1, False)  # concurrent work on the default stream
+    side.synchronize()
+    torch.cuda.synchronize()
+    assert np.array_equal(d_x.cpu().numpy().view(np.uint64), want)
+    assert np.array_equal(d_nodes.cpu().numpy().view(np.uint64), want_nodes)
