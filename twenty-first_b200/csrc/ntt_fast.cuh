@@ -23,7 +23,8 @@
 // Values in flight are lazy (any u64 representative); only the last pass canonicalises on store, so
 // non-canonical input words are accepted as well.
 //
-// Shared-memory layout: tile[col][S] u64 with S = 1060 for 4 columns per CTA (= 4 mod 16: the 16 lanes of a
+// Shared-memory layout: tile[col][S] u64 with S = 1092 for 4 columns per CTA (>= 32 x 34 for the transpose with
+// 16-byte aligned rows; = 4 mod 16: the 16 lanes of a
 // half warp -- 4 columns x 4 rows of the staging pattern -- hit 16 different 8-byte bank pairs; the per-warp
 // column patterns are unit-stride or stride 33).
 #pragma once
@@ -36,6 +37,9 @@ namespace tf21 {
 #endif
 #ifndef TF21_ROW_STORE128
 #define TF21_ROW_STORE128 1  /* 16-byte stores of column pairs in the stage-out loops: 2.92 -> 2.90 ms */
+#endif
+#ifndef TF21_TRANSPOSE_LDS128
+#define TF21_TRANSPOSE_LDS128 1  /* 32 x 32 transpose with row stride 34 and 16-byte read-back: 2.90 -> 2.85 ms */
 #endif
 #ifndef TF21_COL_STORE128
 #define TF21_COL_STORE128 0
@@ -55,7 +59,13 @@ namespace tf21 {
 constexpr u32 kFastCols = TF21_FAST_COLS;  // word-columns (= warps) per CTA: 4, 8 or 16
 // u64 per column slice in shared memory (>= 32 * 33), chosen so that the staging pattern
 // (kFastCols lanes per row segment) is bank-conflict free: S mod 16 = 16 / kFastCols
+#if TF21_TRANSPOSE_LDS128
+constexpr u32 kTransposeStride = 34;
+constexpr u32 kFastS = kFastCols == 4 ? 1092 : kFastCols == 8 ? 1090 : 1089;
+#else
+constexpr u32 kTransposeStride = 33;
 constexpr u32 kFastS = kFastCols == 4 ? 1060 : kFastCols == 8 ? 1058 : 1057;
+#endif
 constexpr u32 kFastThreads = kFastCols * 32;
 constexpr u32 kFastMinBlocks = 16 / kFastCols;  // 512 threads of 128 registers per SM (the 32 x u64 column of a lane needs 64)
 constexpr u32 kStageRowsPerIt = 32 / kFastCols;  // rows covered by one warp instruction of the staging loops
@@ -137,7 +147,7 @@ __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64
         dft32<INV, SHLV>(v);
         const u64 *tw = it ? tw1 : tw0;
         u64 *out = slice + lane;
-        const u32 ss = it ? 32u : 33u;
+        const u32 ss = it ? 32u : kTransposeStride;
         __syncwarp();
         if (tw) {
 #pragma unroll
@@ -154,8 +164,19 @@ __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64
         }
         __syncwarp();
         if (it == 0) {
+#if TF21_TRANSPOSE_LDS128
+            // row stride 34: every row starts 16-byte aligned, the read-back takes 16 LDS.128 instead of 32 LDS.64
+            const ulonglong2 *rowp = reinterpret_cast<const ulonglong2 *>(slice + lane * kTransposeStride);
 #pragma unroll
-            for (int b = 0; b < 32; b++) v[b] = slice[lane * 33 + b];
+            for (int b = 0; b < 16; b++) {
+                const ulonglong2 p = rowp[b];
+                v[2 * b] = p.x;
+                v[2 * b + 1] = p.y;
+            }
+#else
+#pragma unroll
+            for (int b = 0; b < 32; b++) v[b] = slice[lane * kTransposeStride + b];
+#endif
         }
     }
 }
@@ -181,7 +202,7 @@ struct FastColArgs {
 // (ncu: ~890 of 5300 instructions per warp and most `no_instruction` stalls of the general form were staging).
 template <bool INV, bool PLAIN>
 __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kernel(const FastColArgs a) {
-    extern __shared__ u64 smem[];
+    extern __shared__ __align__(16) u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // grid = (column tiles, outer blocks, arrays of the batch): no index divisions
@@ -302,7 +323,7 @@ struct FastRowArgs {
 // fast_coset_interpolate); without it the stage-out loop has no uniform branches.
 template <bool INV, u32 W, bool POST>
 __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kernel(const FastRowArgs a) {
-    extern __shared__ u64 smem[];
+    extern __shared__ __align__(16) u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 rows = a.n1 * a.n2 * a.n3;
@@ -559,7 +580,7 @@ struct FastSingleArgs {
 // warps of an array interleave their 8-byte accesses (stride 24 B): every sector is still used completely.
 template <bool INV, u32 W>
 __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_single_kernel(const FastSingleArgs a) {
-    extern __shared__ u64 smem[];
+    extern __shared__ __align__(16) u64 smem[];
     u64 *tile = smem;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 g = (u64)blockIdx.x * kFastCols + warp;
