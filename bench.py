@@ -120,7 +120,7 @@ def cpu_reference_leg(steps: int, warmup: int, sample_cols: int | None, merkle_l
     o.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cores = o.num_threads()
     n = 1 << LOG2N
-    cols = sample_cols or 128  # half of the 256-column batch: ~1 s of wall time per step on 16 threads
+    cols = sample_cols or COLS_PER_GPU  # the whole 256-column batch of configs[1]: ~2 s of wall time per step on 16 threads
     x = oracle.splitmix64_words(0x210001, n * cols)
     orig = x.copy()
     for _ in range(max(1, min(warmup, 1))):
@@ -141,7 +141,22 @@ def cpu_reference_leg(steps: int, warmup: int, sample_cols: int | None, merkle_l
     for _ in range(reps):
         o.merkle_par_new(leafs)
     merkle_s = (time.perf_counter() - t0) / reps
+    # BASELINE configs[0]: one 2^10-point BFieldElement ntt -> intt round trip, single thread (the reference's own
+    # CPU-runnable case; nearest reference bench shapes are 2^7 / 2^18, benches/ntt.rs:19-21)
+    v = oracle.splitmix64_words(0x210000, 1 << 10)
+    v0 = v.copy()
+    o.ntt(v, 1)
+    o.intt(v, 1)
+    assert np.array_equal(v, v0)
+    reps0 = 2000
+    big = np.tile(v0, reps0)
+    t0 = time.perf_counter()
+    o.ntt_batch(big, 1 << 10, 1, reps0, False, 1)
+    o.ntt_batch(big, 1 << 10, 1, reps0, True, 1)
+    cfg0_us = (time.perf_counter() - t0) / reps0 * 1e6
+    assert np.array_equal(big[: 1 << 10], v0)
     return {
+        "config0_roundtrip_us": cfg0_us,
         "ntt_per_s": ntt_per_s, "ms_per_step": 1e3 * sum(times) / len(times), "cores": cores,
         "sample": f"{cols} columns x 2^{LOG2N} forward+inverse per step; Merkle par_new over 2^{merkle_log2} leaves",
         "merkle_leaves_per_s": (1 << merkle_log2) / merkle_s,
@@ -160,6 +175,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lde", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--cols-total", type=int, default=1024, help="BASELINE configs[4]: columns over all ranks (N > 1)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner)
     # is diverted to stderr for the rest of the run
@@ -174,7 +191,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_leg(args.steps, args.warmup, args.cpu_cols, 22)
+        r = cpu_reference_leg(args.steps, args.warmup, args.cpu_cols or args.cols, 22)
         line = {
             "impl": "reference", "metric": METRIC, "value": r["ntt_per_s"], "unit": "NTT/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
@@ -184,7 +201,8 @@ def main():
                                    "reference algorithm (CPU port) on all host threads",
                        "columns_per_gpu": args.cols, "log2_n": LOG2N, "sample": r["sample"]},
             "cpu_baseline": {"value": r["ntt_per_s"], "unit": "NTT/s", "cores": r["cores"], "kind": "port",
-                             "sample": r["sample"], "merkle_leaves_per_s": r["merkle_leaves_per_s"]},
+                             "sample": r["sample"], "merkle_leaves_per_s": r["merkle_leaves_per_s"],
+                             "config0_2^10_ntt_intt_roundtrip_us_1thread": r["config0_roundtrip_us"]},
             "e2e": {"value": r["ntt_per_s"], "unit": "NTT/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "merkle": {"value": r["merkle_leaves_per_s"], "unit": "leaves/s"},
         }
@@ -203,12 +221,14 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        os.environ["NCCL_DEBUG"] = os.environ.get("TF21_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout
+        # NCCL_DEBUG is left as the launcher set it: stdout was re-pointed at stderr above, so NCCL's banner and
+        # INFO lines cannot reach the JSON line
         dist.init_process_group("nccl", device_id=cuda)
     dev.init(local_rank)
     peak_gbs, peak_src = load_peaks()
     n = 1 << LOG2N
     cols = args.cols
+    P = 0xFFFFFFFF00000001
 
     def barrier():
         if dist is not None:
@@ -232,13 +252,45 @@ def main():
         barrier()
         return max_over_ranks(a.elapsed_time(b))
 
+    def canonical_words(count, seed):
+        """uniform raw words in [0, p) -- the whole range, including [2^63, p) -- as int64 bit patterns"""
+        g = torch.Generator(device=cuda)
+        g.manual_seed(seed)
+        v = torch.randint(-(2**63), 2**63 - 1, (count,), dtype=torch.int64, device=cuda, generator=g)
+        # as u64 the values >= p are the int64 values in [-(2^32 - 1), -1]; v - p = v + 2^32 - 1 (mod 2^64)
+        hi = (v < 0) & (v >= -(2**32 - 1))
+        return torch.where(hi, v + (2**32 - 1), v)
+
+    def column_words(first_col, n_cols, seed):
+        """SplitMix64 stream per global column index (element k of column c = stream seed ^ (c << 32)):
+        a shard regenerates exactly its own columns whatever the number of ranks"""
+        out = torch.empty(n_cols * n, dtype=torch.int64, device=cuda)
+        k = torch.arange(1, n + 1, dtype=torch.int64, device=cuda)
+        GOLD, M1, M2 = -7046029254386353131, -4658895280553007687, -7723592293110705685  # u64 constants as int64
+
+        def lsr(z, sh):
+            return (z >> sh) & ((1 << (64 - sh)) - 1)
+
+        for c in range(n_cols):
+            z = k * GOLD + (seed ^ ((first_col + c) << 32))
+            z = (z ^ lsr(z, 30)) * M1
+            z = (z ^ lsr(z, 27)) * M2
+            z = z ^ lsr(z, 31)
+            hi = (z < 0) & (z >= -(2**32 - 1))
+            out[c * n:(c + 1) * n] = torch.where(hi, z + (2**32 - 1), z)
+        return out
+
+    def u64_sum_mod_p(t):
+        """sum of raw words mod p of an int64 tensor holding u64 bit patterns (exact, via 32-bit halves)"""
+        lo = (t & 0xFFFFFFFF).sum().item()
+        hi = ((t >> 32) & 0xFFFFFFFF).sum().item()
+        return (lo + (hi << 32)) % P
+
     # ---- inputs, resident in HBM (each rank owns its columns / leaves: no data-path collective) ----
-    gen = torch.Generator(device=cuda)
-    gen.manual_seed(0x210001 + rank)
-    x = torch.randint(0, 2**63 - 1, (cols * n,), dtype=torch.int64, device=cuda, generator=gen)  # < p: canonical
+    x = canonical_words(cols * n, 0x210001 + rank)
     x0_check = x[: 4 * n].clone()
     n_leafs = 1 << args.merkle_log2
-    leafs = torch.randint(0, 2**63 - 1, (5 * n_leafs,), dtype=torch.int64, device=cuda, generator=gen)
+    leafs = canonical_words(5 * n_leafs, 0x210002 + 1000 * rank)
     nodes = torch.zeros(10 * n_leafs, dtype=torch.int64, device=cuda)
     roots_all = torch.zeros(5 * world, dtype=torch.int64, device=cuda)
     cap = torch.zeros(10 * world, dtype=torch.int64, device=cuda)
@@ -271,6 +323,34 @@ def main():
     ntt_per_s = transforms_per_step * args.steps / (ntt_ms * 1e-3)
     leaves_per_s = n_leafs * world * args.steps / (merkle_ms * 1e-3)
 
+    # ---- N-rank Merkle root against the oracle (outside the timed region) ---------------------------------
+    # The timed build's root when the whole tree is small enough for the CPU checker, else the same code path
+    # (local build -> cap all-gather -> top levels) over 2^20 leaves per rank.
+    merkle_parity = None
+    if dist is not None:
+        full = n_leafs * world <= (1 << 26)
+        v_leafs = leafs if full else canonical_words(5 << 20, 0x210012 + 1000 * rank)
+        v_nodes = nodes if full else torch.zeros(10 << 20, dtype=torch.int64, device=cuda)
+        dev.merkle_build(v_leafs, v_nodes)
+        dist.all_gather_into_tensor(roots_all, v_nodes[5:10])
+        dev.merkle_build(roots_all, cap)
+        root = cap[5:10].cpu().numpy().view(np.uint64)
+        all_leafs = [torch.empty_like(v_leafs) for _ in range(world)] if rank == 0 else None
+        dist.gather(v_leafs, all_leafs, dst=0)
+        if rank == 0:
+            import oracle
+
+            o = oracle.get(native=True)
+            o.set_num_threads(len(os.sched_getaffinity(0)))
+            host = torch.cat([t.cpu() for t in all_leafs]).numpy().view(np.uint64)
+            rc, want = o.merkle_par_frugal_root(host)
+            merkle_parity = {"ok": bool(rc == 0 and np.array_equal(root, want)), "ranks": world,
+                             "leaves_total": int(host.size // 5), "timed_tree": full,
+                             "checker": "oracle.merkle_par_frugal_root over the concatenated leaves of all ranks"}
+            assert merkle_parity["ok"], "N-rank Merkle root differs from the oracle"
+            del host
+        del all_leafs
+
     # ---- roofline pass: per-launch CUDA-event timing of every kernel in the same steps ------------
     dev.profile_enable(True)
     for _ in range(args.steps):
@@ -291,13 +371,16 @@ def main():
             agg[name] = (tot + ms, cnt + 1)
         return agg
 
-    # DRAM traffic per launch of the dominant kernels, from the committed `ncu --set full` capture of the
-    # same shapes (profiles/r01_ncu_traffic.json, written by tools/ncu_traffic.py); null if absent
-    traffic_db = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic_db = json.load(f)
+    # DRAM traffic per launch of the dominant kernels: NOT measured in this run (ncu replays kernels) but read from
+    # the committed `ncu --set full` capture of the same shapes (profiles/r0X_ncu_traffic.json, tools/ncu_traffic.py)
+    traffic_db, traffic_src = {}, None
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic_db = json.load(f)
+            traffic_src = "profiles/" + name
+            break
 
     def traffic_of(kernel_name, shape_key):
         e = traffic_db.get(shape_key, {})
@@ -313,17 +396,62 @@ def main():
     ntt_alg_bytes = 16 * n * cols
     ntt_avg_ms = ntt_kernel_ms / (2 * args.steps)
     ntt_achieved = ntt_alg_bytes / (ntt_avg_ms * 1e-3) / 1e9
-    dominant = max(ntt_agg.items(), key=lambda kv: kv[1][0])
+    dominant = max(ntt_agg.items(), key=lambda kv: kv[1][0] / kv[1][1])  # the longest average launch
+    ntt_traffic = [traffic_of(k, f"ntt20_cols{cols}") for k in sorted({kk.split("<")[0] for kk in ntt_agg})]
     merkle_agg = by_kernel(merkle_prof)
     merkle_kernel_ms = sum(t for t, _ in merkle_agg.values()) / args.steps
     merkle_alg_bytes = 80 * n_leafs
     merkle_achieved = merkle_alg_bytes / (merkle_kernel_ms * 1e-3) / 1e9
 
+    # ---- BASELINE configs[4]: 1024 x 2^20 columns sharded by column over the ranks (N > 1) ---------------
+    config4 = None
+    if dist is not None and not args.no_cfg4:
+        total_cols = args.cols_total
+        per = total_cols // world
+        del x
+        torch.cuda.empty_cache()
+        first = rank * per
+        y = column_words(first, per, 0x210004)
+        col_sums = [u64_sum_mod_p(y[c * n:(c + 1) * n]) for c in range(0, per, max(1, per // 8))]
+        sums = torch.zeros(world, dtype=torch.int64, device=cuda)
+        my_sum = torch.zeros(1, dtype=torch.int64, device=cuda)
+
+        def cfg4_step():
+            dev.ntt_(y, n, 1, False)
+            dev.ntt_(y, n, 1, True)
+            dist.all_gather_into_tensor(sums, my_sum)  # the only collective of configs[4]: per-shard checksums
+
+        for _ in range(2):
+            cfg4_step()
+        c4_steps = max(1, min(args.steps, 5))
+        c4_ms = timed(cfg4_step, c4_steps)
+        # per-shard 64-bit checksum of the FORWARD transform (wrapping sum of all words) + the DC property
+        # X[0] = sum_j x[j] (mod p) on a sample of columns; the checksum of checksums does not depend on N
+        dev.ntt_(y, n, 1, False)
+        my_sum.copy_(y.sum().reshape(1))
+        dc_ok = all((int(y[c * n].item()) % (1 << 64)) % P == s_ for c, s_ in zip(range(0, per, max(1, per // 8)), col_sums))
+        dist.all_gather_into_tensor(sums, my_sum)
+        dev.ntt_(y, n, 1, True)
+        rt_ok = bool(torch.equal(y[:n], column_words(first, 1, 0x210004)))
+        ok = torch.tensor([int(dc_ok and rt_ok)], device=cuda)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        shard_sums = [int(v) % (1 << 64) for v in sums.cpu().tolist()]
+        config4 = {"workload": f"{total_cols} x 2^{LOG2N}-point BFieldElement NTT then iNTT sharded by column over {world} "
+                               f"B200 ({per} columns per GPU), per-shard checksum all-gather over NCCL (BASELINE configs[4])",
+                   "value": 2 * total_cols * c4_steps / (c4_ms * 1e-3), "unit": "NTT/s", "ms_per_step": c4_ms / c4_steps,
+                   "columns_per_gpu": per, "checksum_of_checksums": f"{sum(shard_sums) % (1 << 64):016x}",
+                   "shard_checksums": [f"{v:016x}" for v in shard_sums],
+                   "parity": {"dc_term_equals_column_sum": bool(ok.item()), "round_trip": bool(ok.item())}}
+        assert ok.item() == 1, "configs[4] parity properties failed"
+        del y
+        torch.cuda.empty_cache()
+        x = canonical_words(cols * n, 0x210001 + rank)
+
     # ---- secondary workload: BASELINE configs[3], coset LDE 2^22 -> 2^26 XFieldElement (rank 0 timing) ----
     lde = None
     if not args.no_lde:
         li, lo = 22, 26
-        vals = torch.randint(0, 2**63 - 1, (3 << li,), dtype=torch.int64, device=cuda, generator=gen)
+        vals = canonical_words(3 << li, 0x210003 + rank)
         out = torch.zeros(3 << lo, dtype=torch.int64, device=cuda)
         g7 = tf.BFieldElement.generator()
         for _ in range(2):
@@ -362,9 +490,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_reference_leg(2, 1, args.cpu_cols, 22)
+        r = cpu_reference_leg(2, 1, args.cpu_cols or args.cols, 22)
         cpu = {"value": r["ntt_per_s"], "unit": "NTT/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
-               "merkle_leaves_per_s": r["merkle_leaves_per_s"]}
+               "merkle_leaves_per_s": r["merkle_leaves_per_s"],
+               "config0_2^10_ntt_intt_roundtrip_us_1thread": r["config0_roundtrip_us"]}
 
     if rank == 0:
         line = {
@@ -374,13 +503,13 @@ def main():
             "config": {"workload": f"batched {cols}x2^{LOG2N}-point BFieldElement NTT then iNTT per GPU (BASELINE configs[1]), "
                                    f"device resident, bit-exact round trip checked",
                        "columns_per_gpu": cols, "log2_n": LOG2N, "l2_policy": "inputs (2 GiB per GPU) larger than L2",
+                       "inputs": "uniform canonical raw words over the whole of [0, p)",
                        "transforms_per_step": transforms_per_step},
             "roofline": {"bound": "hbm", "achieved": ntt_achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": ntt_achieved / peak_gbs,
-                         "traffic": (lambda a, b: (a + b) if (a and b) else None)(
-                             traffic_of("ntt1024_col_kernel", f"ntt20_cols{cols}"),
-                             traffic_of("ntt1024_row_kernel", f"ntt20_cols{cols}")),
-                         "traffic_note": "dram read+write bytes of one col-pass launch + one row-pass launch (ncu)",
+                         "traffic": sum(ntt_traffic) if ntt_traffic and all(ntt_traffic) else None,
+                         "traffic_note": "dram read+write bytes of the launches of one batched transform, from the committed "
+                                         f"ncu --set full capture {traffic_src} of this shape (not re-measured in this run)",
                          "peak_source": peak_src,
                          "kernel": "one batched 2^20 transform = " + " + ".join(sorted(ntt_agg)),
                          "launches_per_transform": launches_per_transform,
@@ -389,14 +518,14 @@ def main():
                          "dominant_kernel": dominant[0],
                          "per_kernel_ms_avg": {k: t / c for k, (t, c) in ntt_agg.items()}},
             "merkle": {"value": leaves_per_s, "unit": "leaves/s", "ms_per_step": merkle_ms / args.steps,
-                       "leaves_per_gpu": n_leafs,
+                       "leaves_per_gpu": n_leafs, "n_rank_root_parity": merkle_parity,
                        "roofline": {"bound": "hbm", "achieved": merkle_achieved, "peak": peak_gbs, "unit": "GB/s",
                                     "frac": merkle_achieved / peak_gbs,
                                     "traffic": traffic_of("tip5_hash10_kernel", f"merkle{args.merkle_log2}"),
-                                    "traffic_note": "dram bytes of the leaf-level tip5_hash10_kernel launch (ncu)",
+                                    "traffic_note": f"dram bytes of the leaf-level launch, committed capture {traffic_src}",
                                     "algorithmic_bytes": merkle_alg_bytes, "kernel_ms": merkle_kernel_ms,
                                     "per_kernel_ms_total": {k: t / args.steps for k, (t, c) in merkle_agg.items()}}},
-            "lde": lde, "cpu_baseline": cpu, "e2e": e2e, "clocks": clock_summary,
+            "config4": config4, "lde": lde, "cpu_baseline": cpu, "e2e": e2e, "clocks": clock_summary,
             "gpu_launches": int(l2 - l0), "gpu_launches_ntt": int(l1 - l0),
         }
         print(json.dumps(line), file=json_out, flush=True)

@@ -19,6 +19,11 @@
  *  - Host-pointer entry points copy host->device->host internally on the calling thread's
  *    current CUDA device.  `*_dev` entry points take device pointers plus a stream
  *    (cudaStream_t passed as void*; NULL = default stream) and are asynchronous.
+ *  - Alignment: device pointers are 8-byte aligned u64 arrays; the Tip5 / Merkle `*_dev` entry points
+ *    (permute, hash_10, merkle_build, merkle_root, mmr_peaks_from_leafs) additionally need their
+ *    INPUT arrays (and the Merkle node array) 16-byte aligned -- cudaMalloc / tf21_malloc / torch
+ *    allocations are; an 8-byte-only view returns TF21_E_BAD_ARG.  The NTT / coset entry points accept
+ *    any 8-byte aligned pointer.
  *  - Thread safe: tables are built once per (device, size) under a lock; scratch is per call
  *    or per (device, stream) cache guarded by a lock.
  *  - There is no CPU fallback: without a usable CUDA device every call returns TF21_E_CUDA.
@@ -45,13 +50,21 @@ enum {
     TF21_E_LEAF_INDEX_INVALID = -9, /* MerkleTreeError::LeafIndexInvalid, merkle_tree.rs:487-489       */
     TF21_E_CAPACITY = -10,       /* output buffer smaller than the result; *count holds the need     */
     TF21_E_DIVISION_BY_ZERO = -11, /* polynomial.rs:556-559 `expect("divisor should be non-zero")` (panic) */
+    TF21_E_NCCL = -12,           /* NCCL failure in a sharded entry point; see tf21_last_cuda_error() */
 };
 
 typedef void *tf21_stream_t; /* cudaStream_t */
 
 /* ---- runtime -------------------------------------------------------------------------------- */
-/* Selects `device` for the calling thread (cudaSetDevice) and uploads the constant tables.      */
-int tf21_init(int device);
+/* Declares how many of the visible devices the sharded entry points use (0 = all) and prepares the
+ * calling thread's current device (constant tables).  Other devices, and the NCCL communicators of the
+ * sharded Merkle build (ncclCommInitAll over devices 0..n-1), are set up on first use.               */
+int tf21_init(int n_devices);
+/* Selects `device` for the calling thread (cudaSetDevice) and prepares it: what a one-process-per-GPU
+ * launch calls with its local rank.                                                                  */
+int tf21_set_device(int device);
+/* Number of devices the sharded entry points will use (min(tf21_init's n_devices, visible)).         */
+int tf21_device_count(void);
 /* Frees cached tables and scratch of every device touched by this process.                     */
 int tf21_shutdown(void);
 const char *tf21_strerror(int code);
@@ -199,9 +212,14 @@ int tf21_merkle_scatter_subtree_dev(const uint64_t *d_local_nodes, uint64_t n_lo
 int tf21_ntt_sharded(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch, int inverse,
                      uint32_t n_shards);
 /* n_shards (a power of two) subtrees built independently, then the top log2(n_shards) levels from the shard
- * roots (the tree cap); nodes_out as tf21_merkle_build.                                                    */
+ * roots (the tree cap); nodes_out as tf21_merkle_build.  With one shard per device (n_shards <= device count)
+ * the cap is exchanged by one ncclAllGather of 40 bytes per device over NVLink and every device hashes the top
+ * levels (TF21_E_NCCL on a NCCL failure); with more shards than devices, or without libnccl, the cap is
+ * assembled in host memory.                                                                                */
 int tf21_merkle_build_sharded(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out,
                               uint32_t n_shards);
+/* 1 if tf21_merkle_build_sharded would gather the cap over NCCL for this shard count, 0 for the host path. */
+int tf21_sharded_uses_nccl(uint32_t n_shards);
 
 /* ---- next wave: authentication structures (merkle_tree.rs:449-542, 614-622) ---- */
 /* MerkleTree::authentication_structure_node_indices: node indices needed to prove the given leaf

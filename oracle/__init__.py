@@ -35,7 +35,7 @@ def build(native: bool = False, force: bool = False) -> str:
     """Compile oracle.c with gcc. native=True uses -march=native (for CPU-baseline timing on
     the box the benchmark runs on) and writes a separate file."""
     out = os.path.join(_BUILD, "liboracle_native.so" if native else "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "field.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "field.h", "tip5_mds_generated.h")]
     if not force and os.path.exists(out) and all(
         os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs
     ):
@@ -82,6 +82,12 @@ class Oracle:
         L.oracle_poly_fast_multiply.argtypes = [_u64p, u64, _u64p, u64, u32, _u64p]
         L.oracle_tip5_permutation.argtypes = [_u64p]
         L.oracle_tip5_permutation.restype = None
+        L.oracle_tip5_hash_rows_batch.argtypes = [_u64p, u64, u64, _u64p, i32]
+        L.oracle_tip5_hash_rows_batch.restype = None
+        L.oracle_tip5_round.argtypes = [_u64p, i32]
+        L.oracle_tip5_round.restype = None
+        L.oracle_tip5_round_naive.argtypes = [_u64p, i32]
+        L.oracle_tip5_round_naive.restype = None
         L.oracle_tip5_hash_10.argtypes = [_u64p, _u64p]
         L.oracle_tip5_hash_10.restype = None
         L.oracle_tip5_hash_pair.argtypes = [_u64p, _u64p, _u64p]
@@ -215,6 +221,11 @@ class Oracle:
         assert state.size == 16
         self.lib.oracle_tip5_permutation(_ptr(state))
 
+    def tip5_round(self, state: np.ndarray, round_index: int, naive: bool = False) -> None:
+        """one round in place: the scalar build's form (mds_generated) or NaiveTip5's (tip5/naive.rs:26-76)"""
+        assert state.size == 16
+        (self.lib.oracle_tip5_round_naive if naive else self.lib.oracle_tip5_round)(_ptr(state), round_index)
+
     def tip5_permute_batch(self, states: np.ndarray, threads: int = 0) -> None:
         self.lib.oracle_tip5_permute_batch(_ptr(states), states.size // 16, threads)
 
@@ -239,6 +250,15 @@ class Oracle:
         inp = np.ascontiguousarray(inp, dtype=np.uint64)
         buf = inp if inp.size else np.zeros(1, dtype=np.uint64)
         self.lib.oracle_tip5_hash_varlen(_ptr(buf), inp.size, _ptr(out))
+        return out
+
+    def hash_rows(self, rows: np.ndarray, threads: int = 0) -> np.ndarray:
+        """hash_varlen of every row of a (n_rows, row_len) matrix -> (n_rows, 5)"""
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        n_rows, row_len = rows.shape
+        out = np.zeros((n_rows, 5), dtype=np.uint64)
+        src = rows if rows.size else np.zeros(1, dtype=np.uint64)
+        self.lib.oracle_tip5_hash_rows_batch(_ptr(src.reshape(-1)), row_len, n_rows, _ptr(out.reshape(-1)), threads)
         return out
 
     def hasher_bytes(self, data: bytes) -> int:

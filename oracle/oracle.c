@@ -14,6 +14,7 @@
  * `&[XFieldElement]` / `&[Digest]` does in memory.
  */
 #include "oracle.h"
+#include "tip5_mds_generated.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -315,18 +316,41 @@ static inline uint64_t split_and_lookup(uint64_t raw) {
     return out;
 }
 
-/* One round, tip5/mod.rs:175-181 with the MDS step in the readable form of
- * tip5/naive.rs:54-68 (the reference's own proptest tip5/naive.rs:94-106 asserts that
- * `mds_generated` + round constants == this for every state and round). */
-static void tip5_round(uint64_t s[STATE_SIZE], int round) {
-    /* sbox_layer, tip5/mod.rs:184-194 */
+/* sbox_layer, tip5/mod.rs:184-194 */
+static inline void tip5_sbox_layer(uint64_t s[STATE_SIZE]) {
     for (int i = 0; i < NUM_SPLIT_AND_LOOKUP; i++) s[i] = split_and_lookup(s[i]);
     for (int i = NUM_SPLIT_AND_LOOKUP; i < STATE_SIZE; i++) {
         uint64_t sq = bfe_mul(s[i], s[i]);
         uint64_t qu = bfe_mul(sq, sq);
         s[i] = bfe_mul(s[i], bfe_mul(sq, qu));
     }
-    /* mds, tip5/naive.rs:54-68 */
+}
+
+/* mds_generated, tip5/mod.rs:210-253: the raw words split into 32-bit halves, each half through the generated
+ * 16-point cyclic convolution (tip5_mds_generated.h <- :256-506, outputs are 16 x the sums), recombined as
+ * (lo >> 4) + (hi << 28) and folded with 2^64 = 2^32 - 1.  Like the reference it may leave a degenerate
+ * representation (>= p), which the round-constant addition corrects (:222-242, tests :1122-1142). */
+static inline void tip5_mds_generated(uint64_t s[STATE_SIZE]) {
+    uint64_t lo[STATE_SIZE], hi[STATE_SIZE], lo2[STATE_SIZE], hi2[STATE_SIZE];
+    for (int i = 0; i < STATE_SIZE; i++) {
+        hi[i] = s[i] >> 32;
+        lo[i] = s[i] & 0xffffffffULL;
+    }
+    tip5_generated_function(lo, lo2);
+    tip5_generated_function(hi, hi2);
+    for (int r = 0; r < STATE_SIZE; r++) {
+        u128 v = (u128)(lo2[r] >> 4) + ((u128)hi2[r] << 28);
+        uint64_t s_hi = (uint64_t)(v >> 64), s_lo = (uint64_t)v;
+        uint64_t add = s_hi * 0xffffffffULL;
+        uint64_t res = s_lo + add;
+        int over = res < s_lo;
+        s[r] = over ? res + 0xffffffffULL : res;
+    }
+}
+
+/* the readable MDS of tip5/naive.rs:54-68 (the reference's differential oracle for mds_generated,
+ * tip5/naive.rs:94-106); kept as the cross-check of the generated form */
+static inline void tip5_mds_naive(uint64_t s[STATE_SIZE]) {
     uint64_t t[STATE_SIZE];
     for (int row = 0; row < STATE_SIZE; row++) {
         uint64_t acc = 0;
@@ -336,8 +360,28 @@ static void tip5_round(uint64_t s[STATE_SIZE], int round) {
         }
         t[row] = acc;
     }
-    /* round constants, tip5/mod.rs:178-180 */
-    for (int i = 0; i < STATE_SIZE; i++) s[i] = bfe_add(t[i], g_rc_raw[round * STATE_SIZE + i]);
+    for (int i = 0; i < STATE_SIZE; i++) s[i] = t[i];
+}
+
+/* One round, tip5/mod.rs:175-181: sbox_layer, mds_generated, += ROUND_CONSTANTS */
+static inline void tip5_round(uint64_t s[STATE_SIZE], int round) {
+    tip5_sbox_layer(s);
+    tip5_mds_generated(s);
+    for (int i = 0; i < STATE_SIZE; i++) s[i] = bfe_add(s[i], g_rc_raw[round * STATE_SIZE + i]);
+}
+
+/* NaiveTip5::round, tip5/naive.rs:26-76 */
+void oracle_tip5_round_naive(uint64_t s[16], int round) {
+    tip5_setup();
+    tip5_sbox_layer(s);
+    tip5_mds_naive(s);
+    for (int i = 0; i < STATE_SIZE; i++) s[i] = bfe_add(s[i], g_rc_raw[round * STATE_SIZE + i]);
+}
+
+/* Tip5::round (scalar build), tip5/mod.rs:175-181 */
+void oracle_tip5_round(uint64_t s[16], int round) {
+    tip5_setup();
+    tip5_round(s, round);
 }
 
 /* Tip5::permutation, tip5/mod.rs:529-533 */
@@ -428,6 +472,18 @@ void oracle_tip5_hash_pairs_batch(const uint64_t *pairs, uint64_t count, uint64_
 #endif
 #pragma omp parallel for schedule(static) num_threads(threads)
     for (uint64_t i = 0; i < count; i++) oracle_tip5_hash_10(pairs + 10 * i, out + 5 * i);
+}
+
+/* hash_varlen of every row of a row-major matrix (the caller-side par_iter pattern, benches/tip5.rs:43-49) */
+void oracle_tip5_hash_rows_batch(const uint64_t *rows, uint64_t row_len, uint64_t n_rows, uint64_t *out, int threads) {
+    tip5_setup();
+#ifdef _OPENMP
+    int nt = threads > 0 ? threads : omp_get_max_threads();
+#pragma omp parallel for num_threads(nt) schedule(static)
+#else
+    (void)threads;
+#endif
+    for (uint64_t i = 0; i < n_rows; i++) oracle_tip5_hash_varlen(rows + i * row_len, row_len, out + 5 * i);
 }
 
 /* Digest -> hex, tip5/digest.rs:85-90,144-152 + b_field_element.rs:615-621:

@@ -47,6 +47,10 @@ int oracle_batch_coset_extrapolate(uint64_t offset_raw, uint64_t n, const uint64
 void oracle_tip5_sample_indices(uint64_t state[16], uint32_t upper_bound, uint64_t num_indices, uint32_t *out);
 
 void oracle_tip5_permutation(uint64_t state[16]);
+/* one round in the scalar build's form (mds_generated, tip5/mod.rs:175-253) and in NaiveTip5's (tip5/naive.rs:26-76) */
+void oracle_tip5_hash_rows_batch(const uint64_t *rows, uint64_t row_len, uint64_t n_rows, uint64_t *out, int threads);
+void oracle_tip5_round(uint64_t state[16], int round);
+void oracle_tip5_round_naive(uint64_t state[16], int round);
 void oracle_tip5_hash_10(const uint64_t in[10], uint64_t out[5]);
 void oracle_tip5_hash_pair(const uint64_t left[5], const uint64_t right[5], uint64_t out[5]);
 void oracle_tip5_hash_varlen(const uint64_t *in, uint64_t len, uint64_t out[5]);

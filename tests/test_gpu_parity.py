@@ -315,8 +315,7 @@ def test_tip5_hash_varlen_and_rows_match_oracle(tf, oracle):
     for row_len, n_rows in ((1, 7), (10, 130), (33, 257), (0, 3), (25, 4097), (7, 20000)):  # <= 4096 rows: 16 lanes per row
         rows = rnd(900 + row_len, row_len * n_rows).reshape(n_rows, row_len)
         got = tf.Tip5.hash_rows(rows)
-        for r in range(0, n_rows, max(1, n_rows // 9)):
-            assert np.array_equal(got[r], oracle.hash_varlen(np.ascontiguousarray(rows[r])))
+        assert np.array_equal(got, oracle.hash_rows(rows)), (row_len, n_rows)  # every row
 
 
 # ---- Merkle -------------------------------------------------------------------------------------------
@@ -409,8 +408,7 @@ def test_tip5_hash_columns_matches_row_hashing(tf, oracle):
         torch.cuda.synchronize()
         got = out.cpu().numpy().view(np.uint64).reshape(n_rows, 5)
         rows = np.ascontiguousarray(cols.T)
-        for r in range(0, n_rows, max(1, n_rows // 13)):
-            assert np.array_equal(got[r], oracle.hash_varlen(np.ascontiguousarray(rows[r])))
+        assert np.array_equal(got, oracle.hash_rows(rows)), (n_rows, n_cols)  # every row
         assert np.array_equal(got, tf.Tip5.hash_rows(rows))
 
 
@@ -802,3 +800,106 @@ def test_device_entry_points_on_a_non_default_stream(tf, oracle):
     torch.cuda.synchronize()
     assert np.array_equal(d_x.cpu().numpy().view(np.uint64), want)
     assert np.array_equal(d_nodes.cpu().numpy().view(np.uint64), want_nodes)
+
+
+def test_shutdown_then_reuse(tf, oracle):
+    """tf21_shutdown frees every cached table; the next call must rebuild them (a stale pointer to a freed
+    twiddle table would give silently wrong transforms at n >= 2^10)"""
+    for log2n in (10, 16, 20):
+        x = rnd(0xAD00 + log2n, 1 << log2n)
+        y = x.copy()
+        tf.ntt(y)  # populate the caches
+    tf.check(tf.lib.tf21_shutdown())
+    for log2n in (10, 16, 20, 22):
+        x = rnd(0xAD10 + log2n, 1 << log2n)
+        want = x.copy()
+        assert oracle.ntt(want, 1) == 0
+        got = x.copy()
+        tf.ntt(got)
+        assert np.array_equal(got, want), log2n
+        tf.intt(got)
+        assert np.array_equal(got, x), log2n
+    leafs = rnd(0xAD20, 5 << 10)
+    rc, want_nodes = oracle.merkle_par_new(leafs)
+    assert np.array_equal(tf.MerkleTree.par_new(leafs.reshape(-1, 5)).nodes.reshape(-1), want_nodes)
+    tf.check(tf.lib.tf21_shutdown())
+    tf.check(tf.lib.tf21_init(0))
+
+
+@pytest.mark.parametrize("log2n", [10, 11, 13, 16, 20, 21])
+def test_ntt_on_an_8_byte_aligned_view(tf, oracle, log2n):
+    """the C ABI promises only u64 alignment: a device view at an odd word offset (8-byte aligned) must not take
+    a 16-byte store path"""
+    import torch
+
+    dev = importlib.import_module("twenty-first_b200.device")
+    n, batch = 1 << log2n, 3
+    x = rnd(0xA110 + log2n, n * batch)
+    want = x.copy()
+    assert oracle.ntt_batch(want, n, 1, batch, False) == 0
+    buf = torch.zeros(n * batch + 1, dtype=torch.int64, device="cuda")
+    view = buf[1:]
+    assert view.data_ptr() % 16 == 8
+    view.copy_(torch.from_numpy(x.view(np.int64)))
+    dev.ntt_(view, n, 1, False)
+    torch.cuda.synchronize()
+    assert np.array_equal(view.cpu().numpy().view(np.uint64), want)
+    dev.ntt_(view, n, 1, True)
+    torch.cuda.synchronize()
+    assert np.array_equal(view.cpu().numpy().view(np.uint64), x)
+
+
+def test_tip5_dev_entry_points_refuse_8_byte_aligned_inputs(tf):
+    import torch
+
+    buf = torch.zeros(1 + 16 * 8, dtype=torch.int64, device="cuda")
+    out = torch.zeros(5 * 8, dtype=torch.int64, device="cuda")
+    odd = buf[1:].data_ptr()
+    assert tf.lib.tf21_tip5_permute_dev(odd, 8, None) == tf.E_BAD_ARG
+    assert tf.lib.tf21_tip5_hash_10_dev(odd, 8, out.data_ptr(), None) == tf.E_BAD_ARG
+    assert tf.lib.tf21_merkle_build_dev(odd, 8, buf.data_ptr(), None) == tf.E_BAD_ARG
+    assert tf.lib.tf21_merkle_root_dev(odd, 8, out.data_ptr(), None) == tf.E_BAD_ARG
+
+
+def test_init_semantics_and_device_count(tf):
+    """tf21_init(n_devices): 0 = all visible; more than visible is refused"""
+    import torch
+
+    visible = torch.cuda.device_count()
+    tf.check(tf.lib.tf21_init(0))
+    assert tf.lib.tf21_device_count() == visible
+    tf.check(tf.lib.tf21_init(1))
+    assert tf.lib.tf21_device_count() == 1
+    assert tf.lib.tf21_sharded_uses_nccl(2) == 0  # one device in use: two shards share it, host-memory cap
+    assert tf.lib.tf21_init(visible + 1) == tf.E_BAD_ARG
+    assert tf.lib.tf21_init(-1) == tf.E_BAD_ARG
+    tf.check(tf.lib.tf21_init(0))
+    tf.check(tf.lib.tf21_set_device(0))
+
+
+def test_sharded_merkle_cap_over_nccl(tf, oracle):
+    """one shard per device: the tree cap crosses devices with one ncclAllGather inside the library (SURVEY.md 8e);
+    the full node array equals the oracle's.  Needs >= 2 visible GPUs (gpurun --gpus 2)."""
+    import torch
+
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    tf.check(tf.lib.tf21_init(0))
+    for n_shards in [s for s in (2, 4, 8) if s <= n_dev]:
+        assert tf.lib.tf21_sharded_uses_nccl(n_shards) == 1
+        for height in (3, 10, 16):
+            n = 1 << height
+            leafs = rnd(0xCC00 + height + n_shards, 5 * n)
+            rc, want_nodes = oracle.merkle_par_new(leafs)
+            assert rc == 0
+            nodes = np.zeros(10 * n, dtype=np.uint64)
+            tf.check(tf.lib.tf21_merkle_build_sharded(leafs.ctypes.data, n, nodes.ctypes.data, n_shards))
+            assert np.array_equal(nodes, want_nodes), (height, n_shards)
+        # columns over the devices, no exchange
+        log2n, batch = 14, 4 * n_shards + 1
+        x = rnd(0xCC50 + n_shards, batch << log2n)
+        want = x.copy()
+        assert oracle.ntt_batch(want, 1 << log2n, 1, batch, False) == 0
+        tf.check(tf.lib.tf21_ntt_sharded(x.ctypes.data, 1 << log2n, 1, batch, 0, n_shards))
+        assert np.array_equal(x, want)

@@ -385,3 +385,22 @@ def test_mmr_bag_peaks_reference_snapshot_and_peak_structure(oracle):
             cnt[1] = oracle.bfe_new(n >> 32)
             want = oracle.hash_pair(peaks[0].copy(), oracle.hash_10(cnt))
             assert np.array_equal(oracle.mmr_bag_peaks(peaks, n), want)
+
+
+def test_tip5_mds_generated_equals_naive_round(oracle):
+    """the reference's own differential test (tip5/naive.rs:94-106): for every state and round the scalar round
+    (sbox_layer + mds_generated + round constants, tip5/mod.rs:175-253) equals NaiveTip5::round -- here over random
+    states, the all-(p-1) state, small values and the degenerate-representation trigger of tip5/mod.rs:222-242"""
+    from oracle import P, splitmix64_words
+
+    states = [splitmix64_words(0x7155 + i, 16) % np.uint64(P) for i in range(200)]
+    states.append(np.full(16, P - 1, dtype=np.uint64))
+    states.append(np.arange(16, dtype=np.uint64))
+    states.append(np.full(16, 0xFFFFFFFF00000000, dtype=np.uint64))
+    for k, st in enumerate(states):
+        for r in range(5):
+            a, b = st.copy(), st.copy()
+            oracle.tip5_round(a, r)
+            oracle.tip5_round(b, r, naive=True)
+            assert np.array_equal(a, b), (k, r)
+            assert (a < np.uint64(P)).all()  # the round-constant addition leaves canonical words (:1122-1142)

@@ -15,6 +15,7 @@ from ._binding import (  # noqa: F401
     E_INCORRECT_NUMBER_OF_LEAFS,
     E_LEAF_INDEX_INVALID,
     E_LEN_NOT_POW2,
+    E_NCCL,
     E_LEN_TOO_LARGE,
     E_ORDER_LE_DEGREE,
     E_TOO_FEW_LEAFS,

@@ -22,6 +22,7 @@ E_BAD_ARG = -8
 E_LEAF_INDEX_INVALID = -9
 E_CAPACITY = -10
 E_DIVISION_BY_ZERO = -11
+E_NCCL = -12
 
 u64 = ctypes.c_uint64
 u32 = ctypes.c_uint32
@@ -31,6 +32,9 @@ vp = ctypes.c_void_p
 # name -> (restype, argtypes); every symbol include/tf21.h declares
 SIGNATURES = {
     "tf21_init": (i32, [i32]),
+    "tf21_set_device": (i32, [i32]),
+    "tf21_device_count": (i32, []),
+    "tf21_sharded_uses_nccl": (i32, [u32]),
     "tf21_shutdown": (i32, []),
     "tf21_strerror": (ctypes.c_char_p, [i32]),
     "tf21_last_cuda_error": (ctypes.c_char_p, []),

@@ -312,6 +312,7 @@ struct FastRowArgs {
     const u64 *t1;
     u64 post_scalar;      // 0 => none
     ScaleTab post;
+    u32 store128;         // host decision: dst and every array of the batch 16-byte aligned (C ABI promises 8 only)
 };
 
 // Last pass of a multi-pass transform.  The passes before it are position preserving, so the source
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kern
         const u64 *tl = tile + c8 * kFastS;
         const u32 op = tc / W;  // element index = op + rows * r
 #if TF21_ROW_STORE128
-        if (tiled && !POST && kFastCols == 4 && (rw & 1) == 0 && a.array_words < (1ull << 29)) {
+        if (a.store128 && tiled && !POST && kFastCols == 4 && (rw & 1) == 0 && a.array_words < (1ull << 29)) {
             // two adjacent word-columns per lane: one 16-byte store per row pair instead of two 8-byte stores
             const u32 cp = lane & 1, rs = lane >> 1;  // 16 rows per warp instruction
             const u64 *t0 = tile + (2 * cp) * kFastS, *t1c = t0 + kFastS;
@@ -987,15 +988,21 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
             a.log_b = log_b;
             a.tw_scalar = tw_scalar;
             a.pre = cur_pre;
-            if (batch > 65535 || n_outer > 65535 || inner_words > (1u << 21)) return TF21_E_LEN_TOO_LARGE;
-            const dim3 grid(a.n_col_tiles, n_outer, (unsigned)batch);
+            if (n_outer > 65535 || inner_words > (1u << 21)) return TF21_E_LEN_TOO_LARGE;
             const bool plain = cur_n_in == n && !cur_pre.lo && tw_full != nullptr;
-            if (inverse) {
-                if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, true>), grid, a, st));
-                else TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, false>), grid, a, st));
-            } else {
-                if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, true>), grid, a, st));
-                else TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, false>), grid, a, st));
+            // the batch index is the z dimension of the grid (<= 65535): larger batches go in slices
+            for (u64 b0 = 0; b0 < batch; b0 += 65535) {
+                const u64 nb = batch - b0 < 65535 ? batch - b0 : 65535;
+                a.src = cur_src + b0 * cur_src_words;
+                a.dst = scratch + b0 * array_words;
+                const dim3 grid(a.n_col_tiles, n_outer, (unsigned)nb);
+                if (inverse) {
+                    if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, true>), grid, a, st));
+                    else TF21_TRY(launch_fast_named("ntt1024_col_kernel<true>", (ntt1024_col_kernel<true, false>), grid, a, st));
+                } else {
+                    if (plain) TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, true>), grid, a, st));
+                    else TF21_TRY(launch_fast_named("ntt1024_col_kernel<false>", (ntt1024_col_kernel<false, false>), grid, a, st));
+                }
             }
         } else {
             SmallColArgs a{};
@@ -1044,6 +1051,9 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     a.t1 = t1;
     a.post_scalar = post_scalar;
     a.post = post;
+    // 16-byte stores need a 16-byte aligned destination for every array of the batch; a view at an odd word offset
+    // (8-byte aligned only) takes the 8-byte path
+    a.store128 = (((uintptr_t)dst & 15) == 0 && (array_words & 1) == 0) ? 1u : 0u;
     dim3 grid;
     if (a.n_tiles && batch <= 65535) {
         grid = dim3(a.n_tiles, (unsigned)batch);

@@ -107,13 +107,32 @@ inline int current_device(int *dev) {
     return 0;
 }
 
+// Tables are read by kernels on caller streams, which may be cudaStreamNonBlocking (host_ntt's own streams, torch
+// side streams) and are then not ordered against the legacy stream.  A cudaMemcpy from pageable memory may return
+// once the data is staged, before the DMA to the device has finished -- so the copy is drained here, before the
+// pointer is published in a cache.
 inline int upload(DeviceTables &t, const std::vector<u64> &host, u64 **out) {
     void *d = nullptr;
     TF21_CUDA(cudaMalloc(&d, host.size() * sizeof(u64)));
-    TF21_CUDA(cudaMemcpy(d, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    cudaError_t e = cudaMemcpy(d, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return cuda_fail(e, "upload", __LINE__);
+    }
     t.owned.push_back(d);
     *out = (u64 *)d;
     return 0;
+}
+
+// free one table of `owned` (used by bounded caches); in-flight kernels may still read it: drain the device first
+inline void release_owned(DeviceTables &t, void *p) {
+    for (auto it = t.owned.begin(); it != t.owned.end(); ++it)
+        if (*it == p) {
+            t.owned.erase(it);
+            break;
+        }
+    cudaFree(p);
 }
 
 // omega_B^{e}, B = 2^lb, as lo[e & (2^h - 1)] * hi[e >> h]
@@ -159,7 +178,12 @@ inline int get_scale_tables(DeviceTables &t, u64 g, u64 c0, u64 count, DeviceTab
         *out = it->second;
         return 0;
     }
-    if (t.scale.size() > 64) {  // bounded cache; tables are small, just forget the keys
+    if (t.scale.size() >= 64) {  // bounded cache: drop every entry and free its tables (kernels in flight on
+        cudaDeviceSynchronize();  // other streams may still read them, so the device is drained first)
+        for (auto &kv : t.scale) {
+            release_owned(t, kv.second.lo);
+            release_owned(t, kv.second.hi);
+        }
         t.scale.clear();
     }
     DeviceTables::Split s;

@@ -1,9 +1,11 @@
 // tf21.cu -- the C ABI of libtf21 (include/tf21.h): argument checking, device state, host<->device
 // staging, and dispatch into the sm_100a kernels.  Single translation unit (the kernels live in the
 // included .cuh files) so the __constant__ tables are shared without relocatable device code.
+#include <dlfcn.h>
+
 #include <algorithm>
-#include <thread>
 #include <cstring>
+#include <thread>
 #include "ntt_fast.cuh"
 #include "tip5_kernels.cuh"
 
@@ -73,6 +75,75 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
     return 0;
 }
 
+// ---- NCCL, bound at run time -------------------------------------------------------------------------
+// The only exchange on the path is the Merkle tree cap (one 40-byte root per shard).  NCCL is
+// dlopen'ed (libnccl.so.2: torch's bundled copy if the process already holds it, else the system one) so that
+// single-GPU users need no NCCL at all; the handful of prototypes below are the stable C API of nccl.h.
+typedef struct ncclComm *tf21_ncclComm_t;
+struct NcclApi {
+    void *handle = nullptr;
+    int (*CommInitAll)(tf21_ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(tf21_ncclComm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, tf21_ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool tried = false;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mutex;
+static std::map<int, std::vector<tf21_ncclComm_t>> g_nccl_comms;  // by device count: communicators of devices 0..n-1
+static int g_n_devices = 0;                                        // tf21_init: devices the sharded entry points use (0 = all)
+constexpr int kNcclUint64 = 5;                                     // ncclUint64, nccl.h
+
+static int nccl_fail(int rc, const char *what) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "NCCL %s: %s", what,
+             (g_nccl.GetErrorString && rc >= 0) ? g_nccl.GetErrorString(rc) : "library not available");
+    return TF21_E_NCCL;
+}
+
+// caller holds g_nccl_mutex
+static bool nccl_load() {
+    if (g_nccl.tried) return g_nccl.handle != nullptr;
+    g_nccl.tried = true;
+    if (getenv("TF21_NO_NCCL")) return false;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return false;
+    g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))dlsym(h, "ncclCommInitAll");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.CommInitAll || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+        dlclose(h);
+        return false;
+    }
+    g_nccl.handle = h;
+    return true;
+}
+
+// communicators over devices 0..n-1 of this process (ncclCommInitAll), created once per n
+static int nccl_comms(int n, tf21_ncclComm_t **out) {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (!nccl_load()) return nccl_fail(-1, "dlopen(libnccl.so.2)");
+    auto it = g_nccl_comms.find(n);
+    if (it == g_nccl_comms.end()) {
+        std::vector<tf21_ncclComm_t> comms(n);
+        std::vector<int> devs(n);
+        for (int i = 0; i < n; i++) devs[i] = i;
+        int prev = 0;
+        cudaGetDevice(&prev);
+        const int rc = g_nccl.CommInitAll(comms.data(), n, devs.data());
+        cudaSetDevice(prev);
+        if (rc != 0) return nccl_fail(rc, "ncclCommInitAll");
+        it = g_nccl_comms.emplace(n, std::move(comms)).first;
+    }
+    *out = it->second.data();
+    return 0;
+}
+
 static int check_ntt_len(u64 n, u32 width) {
     if (width != 1 && width != 3) return TF21_E_BAD_ARG;
     if (n > 0xffffffffull) return TF21_E_LEN_TOO_LARGE;          // ntt.rs:135-136
@@ -80,6 +151,10 @@ static int check_ntt_len(u64 n, u32 width) {
     if (n > (1ull << 30)) return TF21_E_LEN_TOO_LARGE;           // device implementation limit
     return 0;
 }
+
+// the Tip5 kernels read hash inputs / states with 16-byte loads (10 or 16 words per item keep that alignment from
+// an aligned base); a pointer that is only 8-byte aligned is refused instead of faulting on the device
+static inline bool misaligned16(const void *p) { return ((uintptr_t)p & 15) != 0; }
 
 // stream-ordered scratch
 struct Scratch {
@@ -126,13 +201,41 @@ static int ntt_run_locked(DeviceTables &t, const u64 *src, u64 n_in, u64 *dst, u
 
 extern "C" {
 
-int tf21_init(int device) {
+// tf21_init(n_devices), 0 = all visible.  Only the calling thread's current device is prepared here;
+// the other devices (and the NCCL communicators of the sharded Merkle build) are set up on first use, so that a
+// one-process-per-GPU launch (torchrun: every rank sees all eight GPUs) never opens contexts it will not use.
+int tf21_init(int n_devices) {
+    int visible = 0;
+    TF21_CUDA(cudaGetDeviceCount(&visible));
+    if (n_devices < 0 || n_devices > visible) return TF21_E_BAD_ARG;
+    {
+        std::lock_guard<std::mutex> lock(g_nccl_mutex);
+        g_n_devices = n_devices;
+    }
+    DeviceTables *t;
+    return get_tables(&t);
+}
+
+int tf21_set_device(int device) {
     TF21_CUDA(cudaSetDevice(device));
     DeviceTables *t;
     return get_tables(&t);
 }
 
+int tf21_device_count(void) {
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess) return 0;
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    return (g_n_devices > 0 && g_n_devices < visible) ? g_n_devices : visible;
+}
+
 int tf21_shutdown(void) {
+    {
+        std::lock_guard<std::mutex> nlock(g_nccl_mutex);
+        for (auto &kv : g_nccl_comms)
+            for (auto c : kv.second) g_nccl.CommDestroy(c);
+        g_nccl_comms.clear();
+    }
     std::lock_guard<std::mutex> lock(g_mutex);
     int prev = -1;
     cudaGetDevice(&prev);
@@ -142,6 +245,7 @@ int tf21_shutdown(void) {
         for (void *p : kv.second.owned) cudaFree(p);
     }
     g_devices.clear();
+    g_fast_tables.clear();  // their device pointers lived in `owned` and are gone: never hand them out again
     if (prev >= 0) cudaSetDevice(prev);
     return 0;
 }
@@ -162,6 +266,7 @@ const char *tf21_strerror(int code) {
         case TF21_E_LEAF_INDEX_INVALID: return "MerkleTreeError::LeafIndexInvalid";
         case TF21_E_CAPACITY: return "output buffer too small";
         case TF21_E_DIVISION_BY_ZERO: return "divisor should be non-zero";
+        case TF21_E_NCCL: return "NCCL error (see tf21_last_cuda_error)";
         default: return "unknown tf21 error";
     }
 }
@@ -708,11 +813,13 @@ int tf21_batch_coset_extrapolate(uint64_t offset_raw, uint64_t codeword_length, 
 
 // ---- Tip5 ------------------------------------------------------------------------------------------
 int tf21_tip5_permute_dev(uint64_t *d_states, uint64_t count, tf21_stream_t stream) {
+    if (count && (!d_states || misaligned16(d_states))) return TF21_E_BAD_ARG;
     DeviceTables *t;
     TF21_TRY(get_tables(&t));
     return launch_permute(d_states, count, (cudaStream_t)stream);
 }
 int tf21_tip5_hash_10_dev(const uint64_t *d_in, uint64_t count, uint64_t *d_out, tf21_stream_t stream) {
+    if (count && (!d_in || !d_out || misaligned16(d_in))) return TF21_E_BAD_ARG;
     DeviceTables *t;
     TF21_TRY(get_tables(&t));
     return launch_hash10(d_in, count, d_out, (cudaStream_t)stream);
@@ -798,6 +905,7 @@ int tf21_tip5_hash_varlen(const uint64_t *in, uint64_t len, uint64_t out[5]) {
 int tf21_merkle_build_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d_nodes_out, tf21_stream_t stream) {
     TF21_TRY(check_leaf_count(n_leafs));
     if (!d_leafs || !d_nodes_out) return TF21_E_BAD_ARG;
+    if (misaligned16(d_leafs) || misaligned16(d_nodes_out)) return TF21_E_BAD_ARG;
     DeviceTables *t;
     TF21_TRY(get_tables(&t));
     return merkle_build_dev(d_leafs, n_leafs, d_nodes_out, (cudaStream_t)stream);
@@ -805,7 +913,7 @@ int tf21_merkle_build_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d
 
 int tf21_merkle_root_dev(const uint64_t *d_leafs, uint64_t n_leafs, uint64_t *d_root_out, tf21_stream_t stream) {
     TF21_TRY(check_leaf_count(n_leafs));
-    if (!d_leafs || !d_root_out) return TF21_E_BAD_ARG;
+    if (!d_leafs || !d_root_out || misaligned16(d_leafs)) return TF21_E_BAD_ARG;
     DeviceTables *t;
     TF21_TRY(get_tables(&t));
     cudaStream_t st = (cudaStream_t)stream;
@@ -931,7 +1039,7 @@ int tf21_mmr_peaks_from_leafs_dev(const uint64_t *d_leafs, uint64_t n_leafs, uin
     if (!n_peaks) return TF21_E_BAD_ARG;
     *n_peaks = (u64)__builtin_popcountll(n_leafs);
     if (n_leafs == 0) return 0;
-    if (!d_leafs || !d_peaks_out) return TF21_E_BAD_ARG;
+    if (!d_leafs || !d_peaks_out || misaligned16(d_leafs)) return TF21_E_BAD_ARG;
     if (n_leafs > (1ull << 40)) return TF21_E_ALLOC;
     DeviceTables *t;
     TF21_TRY(get_tables(&t));
@@ -992,6 +1100,7 @@ int tf21_mmr_bag_peaks(const uint64_t *peaks, uint64_t n_peaks, uint64_t leaf_co
 // Shard s runs on device s % n_devices, so the index algebra is testable on a single GPU.
 static int visible_devices(int *n) {
     TF21_CUDA(cudaGetDeviceCount(n));
+    *n = tf21_device_count();  // honours tf21_init(n_devices)
     return *n > 0 ? 0 : TF21_E_CUDA;
 }
 
@@ -1026,14 +1135,11 @@ int tf21_ntt_sharded(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch,
     return 0;
 }
 
-int tf21_merkle_build_sharded(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out, uint32_t n_shards) {
-    TF21_TRY(check_leaf_count(n_leafs));
-    if (!leafs || !nodes_out) return TF21_E_BAD_ARG;
-    if (n_shards == 0 || (n_shards & (n_shards - 1))) return TF21_E_BAD_ARG;  // subtrees are powers of two
-    while (n_shards > 1 && n_leafs / n_shards < 1) n_shards >>= 1;
-    if (n_shards == 1) return tf21_merkle_build(leafs, n_leafs, nodes_out);
-    int n_dev = 0, prev = 0;
-    TF21_TRY(visible_devices(&n_dev));
+// host path of the sharded build (no NCCL, or several shards per device): the shard trees come back to host
+// memory, the cap is finished from the shard roots there
+static int merkle_build_sharded_host(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out, uint32_t n_shards,
+                                     int n_dev) {
+    int prev = 0;
     cudaGetDevice(&prev);
     const u64 local = n_leafs / n_shards;
     std::vector<int> rc(n_shards, 0);
@@ -1062,6 +1168,118 @@ int tf21_merkle_build_sharded(const uint64_t *leafs, uint64_t n_leafs, uint64_t 
     TF21_TRY(tf21_merkle_build(nodes_out + 5 * n_shards, n_shards, cap.data()));
     std::memcpy(nodes_out, cap.data(), 5 * n_shards * sizeof(u64));  // includes nodes[0] = 0
     return 0;
+}
+
+// One shard per device: every device builds its subtree (merkle_tree.rs:247-275), the shard roots -- the tree cap --
+// are exchanged with ONE ncclAllGather of 40 bytes per rank over NVLink, and every device hashes the top
+// log2(n_shards) levels itself.  Nothing but the cap crosses devices.
+static int merkle_build_sharded_nccl(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out, uint32_t n_shards) {
+    tf21_ncclComm_t *comms = nullptr;
+    TF21_TRY(nccl_comms((int)n_shards, &comms));
+    const u64 local = n_leafs / n_shards;
+    struct Shard {
+        cudaStream_t st = nullptr;
+        u64 *d_leafs = nullptr, *d_nodes = nullptr, *d_roots = nullptr, *d_cap = nullptr;
+        int rc = 0;
+    };
+    std::vector<Shard> sh(n_shards);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    auto on_all = [&](auto &&fn) {
+        std::vector<std::thread> workers;
+        for (uint32_t i = 0; i < n_shards; i++)
+            workers.emplace_back([&, i] {
+                if (sh[i].rc) return;
+                if (cudaSetDevice((int)i) != cudaSuccess) {
+                    sh[i].rc = cuda_fail(cudaGetLastError(), "cudaSetDevice", __LINE__);
+                    return;
+                }
+                sh[i].rc = fn(i, sh[i]);
+            });
+        for (auto &w : workers) w.join();
+    };
+    auto first_error = [&]() {
+        for (auto &x : sh)
+            if (x.rc) return x.rc;
+        return 0;
+    };
+    // phase 1: local subtrees, device resident
+    on_all([&](uint32_t i, Shard &x) -> int {
+        TF21_CUDA(cudaStreamCreateWithFlags(&x.st, cudaStreamNonBlocking));
+        TF21_CUDA(cudaMalloc((void **)&x.d_leafs, 5 * local * sizeof(u64)));
+        TF21_CUDA(cudaMalloc((void **)&x.d_nodes, 10 * local * sizeof(u64)));
+        TF21_CUDA(cudaMalloc((void **)&x.d_roots, 5 * n_shards * sizeof(u64)));
+        TF21_CUDA(cudaMalloc((void **)&x.d_cap, 10 * n_shards * sizeof(u64)));
+        TF21_CUDA(cudaMemcpyAsync(x.d_leafs, leafs + 5 * i * local, 5 * local * sizeof(u64), cudaMemcpyHostToDevice, x.st));
+        TF21_TRY(tf21_merkle_build_dev(x.d_leafs, local, x.d_nodes, (tf21_stream_t)x.st));
+        TF21_CUDA(cudaStreamSynchronize(x.st));
+        return 0;
+    });
+    int rc = first_error();
+    // phase 2: the cap -- one all-gather of the shard roots (nodes[1] of every local tree), launched as one group
+    if (!rc) {
+        int nrc = g_nccl.GroupStart();
+        for (uint32_t i = 0; i < n_shards && nrc == 0; i++)
+            nrc = g_nccl.AllGather(sh[i].d_nodes + 5, sh[i].d_roots, 5, kNcclUint64, comms[i], sh[i].st);
+        const int erc = g_nccl.GroupEnd();
+        if (nrc == 0) nrc = erc;
+        if (nrc != 0) rc = nccl_fail(nrc, "ncclAllGather");
+    }
+    // phase 3: every device finishes the top of the tree from the gathered cap; results go home
+    if (!rc) {
+        on_all([&](uint32_t i, Shard &x) -> int {
+            TF21_TRY(tf21_merkle_build_dev(x.d_roots, n_shards, x.d_cap, (tf21_stream_t)x.st));
+            for (u64 wd = 1; wd <= local; wd <<= 1)
+                TF21_CUDA(cudaMemcpyAsync(nodes_out + 5 * (n_shards * wd + i * wd), x.d_nodes + 5 * wd,
+                                          5 * wd * sizeof(u64), cudaMemcpyDeviceToHost, x.st));
+            if (i == 0)  // nodes[0] = 0 and nodes[1 .. n_shards): identical on every device, device 0 reports them
+                TF21_CUDA(cudaMemcpyAsync(nodes_out, x.d_cap, 5 * n_shards * sizeof(u64), cudaMemcpyDeviceToHost, x.st));
+            TF21_CUDA(cudaStreamSynchronize(x.st));
+            return 0;
+        });
+        rc = first_error();
+    }
+    for (uint32_t i = 0; i < n_shards; i++) {
+        cudaSetDevice((int)i);
+        if (sh[i].st) cudaStreamSynchronize(sh[i].st);
+        cudaFree(sh[i].d_leafs);
+        cudaFree(sh[i].d_nodes);
+        cudaFree(sh[i].d_roots);
+        cudaFree(sh[i].d_cap);
+        if (sh[i].st) cudaStreamDestroy(sh[i].st);
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int tf21_merkle_build_sharded(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out, uint32_t n_shards) {
+    TF21_TRY(check_leaf_count(n_leafs));
+    if (!leafs || !nodes_out) return TF21_E_BAD_ARG;
+    if (n_shards == 0 || (n_shards & (n_shards - 1))) return TF21_E_BAD_ARG;  // subtrees are powers of two
+    while (n_shards > 1 && n_leafs / n_shards < 1) n_shards >>= 1;
+    if (n_shards == 1) return tf21_merkle_build(leafs, n_leafs, nodes_out);
+    int n_dev = 0;
+    TF21_TRY(visible_devices(&n_dev));
+    // one shard per device: the cap travels over NCCL.  More shards than devices (index algebra testable on one
+    // GPU), TF21_NO_NCCL, or no libnccl at all: the cap is assembled in host memory.
+    if ((int)n_shards <= n_dev && !getenv("TF21_NO_NCCL")) {
+        const int rc = merkle_build_sharded_nccl(leafs, n_leafs, nodes_out, n_shards);
+        bool have_nccl;
+        {
+            std::lock_guard<std::mutex> lock(g_nccl_mutex);
+            have_nccl = g_nccl.handle != nullptr;
+        }
+        if (rc != TF21_E_NCCL || have_nccl) return rc;  // a real NCCL failure is reported, a missing library is not
+    }
+    return merkle_build_sharded_host(leafs, n_leafs, nodes_out, n_shards, n_dev);
+}
+
+/* which path tf21_merkle_build_sharded takes for this shard count: 1 = NCCL cap gather, 0 = host-memory cap */
+int tf21_sharded_uses_nccl(uint32_t n_shards) {
+    int n_dev = 0;
+    if (visible_devices(&n_dev) != 0 || n_shards < 2 || (int)n_shards > n_dev || getenv("TF21_NO_NCCL")) return 0;
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    return nccl_load() ? 1 : 0;
 }
 
 int tf21_merkle_build(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_out) {

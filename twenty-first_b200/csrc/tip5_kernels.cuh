@@ -93,6 +93,7 @@ inline int upload_tip5_constants() {
     TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc_lo, lo, sizeof(lo)));
     TF21_CUDA(cudaMemcpyToSymbol(c_tip5_rc_hi, hi, sizeof(hi)));
     TF21_CUDA(cudaMemcpyToSymbol(c_tip5_lut, lut, sizeof(lut)));
+    TF21_CUDA(cudaStreamSynchronize(nullptr));  // pageable sources: drain before kernels on non-blocking streams read them
     return 0;
 }
 

@@ -17,7 +17,8 @@ def _stream():
 
 
 def init(device: int) -> None:
-    B.check(B.lib.tf21_init(device))
+    """one process per GPU: select `device` for this thread and prepare it (tf21_set_device)"""
+    B.check(B.lib.tf21_set_device(device))
 
 
 def ntt_(data: torch.Tensor, n: int, width: int = 1, inverse: bool = False) -> None:
