@@ -92,6 +92,11 @@ int tf21_stream_sync(tf21_stream_t stream);
 int tf21_selftest_field_dev(int op, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out,
                             uint64_t n, tf21_stream_t stream);
 
+/* Diagnostic: lands n_tiles [1024 rows][4 words] tiles of a [1024][inner_words] device matrix (16-byte aligned)
+ * by TMA and returns the raw shared-memory image of each (4096 words), which pins the swizzled tile layout. */
+int tf21_selftest_tma_tile_dev(const uint64_t *d_matrix, uint64_t inner_words, uint64_t n_tiles,
+                               uint64_t *d_out, tf21_stream_t stream);
+
 /* ---- NTT: math::ntt::ntt / intt (ntt.rs:67-82, 109-125) ------------------------------------- */
 /* In place over `batch` contiguous arrays of n*width words. n == 0 or 1 is a no-op.
  * out[i] = sum_j x[j] * omega_n^(i j), natural order in and out; intt also multiplies by n^-1.  */

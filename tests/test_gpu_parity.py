@@ -903,3 +903,22 @@ def test_sharded_merkle_cap_over_nccl(tf, oracle):
         assert oracle.ntt_batch(want, 1 << log2n, 1, batch, False) == 0
         tf.check(tf.lib.tf21_ntt_sharded(x.ctypes.data, 1 << log2n, 1, batch, 0, n_shards))
         assert np.array_equal(x, want)
+
+
+def test_tma_tile_layout_matches_the_swizzle_formula(tf):
+    """the column pass reads and writes its [1024 rows][4 words] tile in the layout TMA produces with
+    CU_TENSOR_MAP_SWIZZLE_32B: word (r, c) at 4 r + 2 ((c >> 1) ^ ((r >> 2) & 1)) + (c & 1) (csrc/tma.cuh)"""
+    import torch
+
+    inner, n_tiles = 16, 4
+    m = torch.arange(1024 * inner, dtype=torch.int64, device="cuda")
+    out = torch.zeros(n_tiles * 4096, dtype=torch.int64, device="cuda")
+    tf.check(tf.lib.tf21_selftest_tma_tile_dev(m.data_ptr(), inner, n_tiles, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(n_tiles, 4096)
+    r, c = np.meshgrid(np.arange(1024), np.arange(4), indexing="ij")
+    idx = 4 * r + 2 * ((c >> 1) ^ ((r >> 2) & 1)) + (c & 1)
+    for t in range(n_tiles):
+        want = np.zeros(4096, dtype=np.int64)
+        want[idx.reshape(-1)] = (r * inner + 4 * t + c).reshape(-1)
+        assert np.array_equal(got[t], want), t

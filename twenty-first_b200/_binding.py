@@ -47,6 +47,7 @@ SIGNATURES = {
     "tf21_memcpy_d2h": (i32, [vp, vp, u64, vp]),
     "tf21_stream_sync": (i32, [vp]),
     "tf21_selftest_field_dev": (i32, [i32, vp, vp, vp, u64, vp]),
+    "tf21_selftest_tma_tile_dev": (i32, [vp, u64, u64, vp, vp]),
     "tf21_ntt": (i32, [vp, u64, u32, u64]),
     "tf21_intt": (i32, [vp, u64, u32, u64]),
     "tf21_ntt_dev": (i32, [vp, u64, u32, u64, i32, vp]),

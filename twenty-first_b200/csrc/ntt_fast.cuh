@@ -29,6 +29,7 @@
 // column patterns are unit-stride or stride 33).
 #pragma once
 #include "ntt_kernels.cuh"
+#include "tma.cuh"
 
 namespace tf21 {
 
@@ -140,14 +141,19 @@ __device__ __forceinline__ u64 scale_factor_l(const ScaleTab &t, u64 idx) {
 // out: slice[i] = X[i] * (tw1 ? tw1[32 (i >> 5)] : 1), i = lane + 32 k2   (any u64)
 // slice: this warp's kFastS-word shared-memory slice; tw0 = t1 + lane with t1[k1*32+b] = w1024^(k1 b);
 // tw1: per-lane pointer into the inter-pass twiddle row (or nullptr).
-template <bool INV, bool MASKMUL = false, int SHLV = TF21_SHL_WIDE>
-__device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64 *tw0, const u64 *tw1, u32 lane) {
+// TILE_OUT (TMA column pass): the second step stores X[lane + 32 k2] at out1[k2 * ss1] -- the swizzled tile that
+// goes back to HBM as one box store -- after a CTA barrier, because that tile overlaps the private transpose
+// slices of the other warps.
+template <bool INV, bool MASKMUL = false, int SHLV = TF21_SHL_WIDE, bool TILE_OUT = false>
+__device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64 *tw0, const u64 *tw1, u32 lane,
+                                             u64 *out1 = nullptr, u32 ss1 = 32u) {
 #pragma unroll 1
     for (int it = 0; it < 2; it++) {
         dft32<INV, SHLV>(v);
         const u64 *tw = it ? tw1 : tw0;
-        u64 *out = slice + lane;
-        const u32 ss = it ? 32u : kTransposeStride;
+        u64 *out = (TILE_OUT && it) ? out1 : slice + lane;
+        const u32 ss = it ? (TILE_OUT ? ss1 : 32u) : kTransposeStride;
+        if (TILE_OUT && it) __syncthreads();  // every warp has read its transposed column back
         __syncwarp();
         if (tw) {
 #pragma unroll
@@ -298,6 +304,82 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_col_kern
             dst[r * row_words] = tl[r];
         }
     }
+}
+
+// ---- column pass with TMA staging (the batched 2^20 transform and every PLAIN column pass) ----------------------
+struct ColTmaArgs {
+    const u64 *t1;       // [32][32] omega_1024^(k1 b)
+    const u64 *tw_full;  // [inner_elems][1024] inter-pass twiddles (times n^-1 for the inverse first pass)
+    u32 w;               // 1 | 3
+    u32 slab0;           // first slab (array x outer block) of this launch: grid.y is limited to 65535
+};
+
+constexpr u32 kTmaTileWords = 1024 * kTmaTileCols;                       // 32 KiB
+constexpr size_t kColTmaSmem = kFastSmem + 1024 /* alignment slack */ + 16 /* mbarrier */;
+
+// Same arithmetic as ntt1024_col_kernel<INV, true>; the tile travels by TMA.  Shared memory: one region that is
+// first the landing zone of the four box loads ([1024 rows][4 words], SWIZZLE_32B), then -- after every warp has
+// pulled its column into registers -- the four private transpose slices, and finally the outgoing tile.
+template <bool INV>
+__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks)
+    ntt1024_col_tma_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map,
+                           const ColTmaArgs a) {
+    static_assert(kFastCols == kTmaTileCols, "one warp per word-column of the tile");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // the swizzle pattern is a function of the absolute shared-memory address: align the tile to 1 KiB
+    // (offset arithmetic on the shared array, so that the accesses stay LDS / STS rather than generic)
+    u64 *tile = reinterpret_cast<u64 *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    u64 *bar = tile + kFastCols * kFastS;  // 8-byte aligned, behind the private slices
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 ct = blockIdx.x, slab = a.slab0 + blockIdx.y;
+    if (tid == 0) {
+        tma_prefetch_map(&src_map);
+        tma_prefetch_map(&dst_map);
+        mbar_init(bar, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, kTmaTileWords * 8);
+#pragma unroll
+        for (u32 q = 0; q < 1024 / kTmaBoxRows; q++)
+            tma_load_3d(tile + q * kTmaBoxRows * kTmaTileCols, &src_map, ct * kTmaTileCols, q * kTmaBoxRows, slab, bar);
+    }
+    // word (row 32 a + lane, column warp) = tile[off0 + 128 a]: the swizzle bit depends on the lane only
+    const u32 off0 = tma_tile_word(lane, warp);
+    const u32 qw = ct * kTmaTileCols + warp;
+    const u64 jrest = a.w == 1 ? qw : qw / 3u;
+    mbar_wait(bar, 0);
+    u64 v[32];
+#pragma unroll
+    for (int aa = 0; aa < 32; aa++) v[aa] = tile[off0 + 128 * aa];
+    __syncthreads();  // the landing zone is dead: it becomes the private slices
+    dft1024_warp<INV, TF21_COL_MASKMUL, TF21_SHL_COL, true>(v, tile + warp * kFastS, a.t1 + lane,
+                                                            a.tw_full + jrest * 1024 + lane, lane, tile + off0, 128u);
+    fence_proxy_async_smem();  // my generic-proxy writes of the outgoing tile -> visible to the TMA engine
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (u32 q = 0; q < 1024 / kTmaBoxRows; q++)
+            tma_store_3d(&dst_map, ct * kTmaTileCols, q * kTmaBoxRows, slab, tile + q * kTmaBoxRows * kTmaTileCols);
+        tma_store_commit();
+        tma_store_wait_read();  // shared memory must stay valid until the engine has read it
+    }
+}
+
+// diagnostic (tests): land one tile by TMA and copy the raw shared-memory image out, to pin the swizzle formula
+__global__ void __launch_bounds__(128) tma_tile_probe_kernel(const __grid_constant__ CUtensorMap src_map, u64 *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *tile = reinterpret_cast<u64 *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    u64 *bar = tile + kTmaTileWords;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, kTmaTileWords * 8);
+        for (u32 q = 0; q < 1024 / kTmaBoxRows; q++)
+            tma_load_3d(tile + q * kTmaBoxRows * kTmaTileCols, &src_map, blockIdx.x * kTmaTileCols, q * kTmaBoxRows, 0, bar);
+    }
+    mbar_wait(bar, 0);
+    for (u32 i = threadIdx.x; i < kTmaTileWords; i += blockDim.x) out[(u64)blockIdx.x * kTmaTileWords + i] = tile[i];
 }
 
 struct FastRowArgs {
@@ -709,6 +791,12 @@ inline int get_tw_small(DeviceTables &t, int dev, unsigned log_b, unsigned log_n
     return 0;
 }
 
+// TF21_NO_TMA=1 in the environment keeps the LDGSTS-staged column pass (A/B runs, tools/ab.sh)
+inline bool tma_disabled() {
+    static const bool off = getenv("TF21_NO_TMA") != nullptr;
+    return off;
+}
+
 template <typename K, typename A>
 inline int launch_fast_named(const char *name, K kernel, dim3 grid, const A &args, cudaStream_t st) {
     TF21_LAUNCH_NAMED(name, kernel, grid, kFastThreads, kFastSmem, st, args);
@@ -990,6 +1078,33 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
             a.pre = cur_pre;
             if (n_outer > 65535 || inner_words > (1u << 21)) return TF21_E_LEN_TOO_LARGE;
             const bool plain = cur_n_in == n && !cur_pre.lo && tw_full != nullptr;
+            // PLAIN column passes move their tiles by TMA: source and scratch are [batch * n_outer][1024][inner_words]
+            // tensors (source arrays are n * w words apart when every input row exists)
+            if (plain && !tma_disabled()) {
+                CUtensorMap src_map, dst_map;
+                const u64 slabs = batch * n_outer;
+                if (tma_encode_tile_map(&src_map, cur_src, inner_words, slabs) &&
+                    tma_encode_tile_map(&dst_map, scratch, inner_words, slabs)) {
+                    ColTmaArgs ta{t1, tw_full, w, 0};
+                    for (u64 s0 = 0; s0 < slabs; s0 += 65535) {
+                        ta.slab0 = (u32)s0;
+                        const dim3 grid((unsigned)(inner_words / kTmaTileCols),
+                                        (unsigned)(slabs - s0 < 65535 ? slabs - s0 : 65535));
+                        if (inverse)
+                            TF21_LAUNCH_NAMED("ntt1024_col_tma_kernel<true>", (ntt1024_col_tma_kernel<true>), grid,
+                                              kFastThreads, kColTmaSmem, st, src_map, dst_map, ta);
+                        else
+                            TF21_LAUNCH_NAMED("ntt1024_col_tma_kernel<false>", (ntt1024_col_tma_kernel<false>), grid,
+                                              kFastThreads, kColTmaSmem, st, src_map, dst_map, ta);
+                    }
+                    consumed += lp;
+                    cur_src = scratch;
+                    cur_src_words = array_words;
+                    cur_n_in = n;
+                    cur_pre = ScaleTab{nullptr, nullptr, 0};
+                    continue;
+                }
+            }
             // the batch index is the z dimension of the grid (<= 65535): larger batches go in slices
             for (u64 b0 = 0; b0 < batch; b0 += 65535) {
                 const u64 nb = batch - b0 < 65535 ? batch - b0 : 65535;

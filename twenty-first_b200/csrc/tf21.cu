@@ -65,6 +65,9 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
         TF21_FAST_SMEM((ntt1024_row_kernel<true, 3, false>));
         TF21_FAST_SMEM((ntt1024_row_kernel<true, 3, true>));
 #undef TF21_FAST_SMEM
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
+        TF21_CUDA(cudaFuncSetAttribute(tma_tile_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTmaTileWords * 8 + 1024 + 16)));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
@@ -360,6 +363,20 @@ int tf21_selftest_field_dev(int op, const uint64_t *d_a, const uint64_t *d_b, ui
                             tf21_stream_t stream) {
     if (n == 0) return 0;
     TF21_LAUNCH(selftest_field_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, op, d_a, d_b, d_out, n);
+    return 0;
+}
+
+// lands n_tiles tiles ([1024 rows][4 words] each, tile t = word-columns 4t..4t+3 of a [1024][inner_words] matrix) by
+// TMA and returns the raw shared-memory images (4096 words per tile): pins the swizzle formula of tma.cuh
+int tf21_selftest_tma_tile_dev(const uint64_t *d_matrix, uint64_t inner_words, uint64_t n_tiles, uint64_t *d_out,
+                               tf21_stream_t stream) {
+    if (!d_matrix || !d_out || n_tiles == 0 || n_tiles * kTmaTileCols > inner_words) return TF21_E_BAD_ARG;
+    DeviceTables *t;
+    TF21_TRY(get_tables(&t));
+    CUtensorMap map;
+    if (!tma_encode_tile_map(&map, d_matrix, inner_words, 1)) return TF21_E_BAD_ARG;
+    TF21_LAUNCH(tma_tile_probe_kernel, (unsigned)n_tiles, 128, kTmaTileWords * 8 + 1024 + 16, (cudaStream_t)stream, map,
+                d_out);
     return 0;
 }
 
