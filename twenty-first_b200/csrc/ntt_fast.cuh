@@ -144,7 +144,7 @@ __device__ __forceinline__ u64 scale_factor_l(const ScaleTab &t, u64 idx) {
 // TILE_OUT (TMA column pass): the second step stores X[lane + 32 k2] at out1[k2 * ss1] -- the swizzled tile that
 // goes back to HBM as one box store -- after a CTA barrier, because that tile overlaps the private transpose
 // slices of the other warps.
-template <bool INV, bool MASKMUL = false, int SHLV = TF21_SHL_WIDE, bool TILE_OUT = false>
+template <bool INV, bool MASKMUL = false, int SHLV = TF21_SHL_WIDE, bool TILE_OUT = false, bool CANON_OUT = false>
 __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64 *tw0, const u64 *tw1, u32 lane,
                                              u64 *out1 = nullptr, u32 ss1 = 32u) {
 #pragma unroll 1
@@ -164,6 +164,9 @@ __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64
                 }
                 out[k * ss] = MASKMUL ? gl_mul_mask(v[brev5(k)], __ldg(tw + 32 * k)) : gl_mul(v[brev5(k)], __ldg(tw + 32 * k));
             }
+        } else if (CANON_OUT && it) {  // last pass: canonical words straight into the outgoing tile
+#pragma unroll
+            for (int k = 0; k < 32; k++) out[k * ss] = gl_canonw(v[brev5(k)]);
         } else {
 #pragma unroll
             for (int k = 0; k < 32; k++) out[k * ss] = v[brev5(k)];
@@ -491,6 +494,48 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_row_kern
     }
 }
 
+// ---- last (transposing) pass with a TMA store ----------------------------------------------------------------
+struct RowTmaArgs {
+    const u64 *src;
+    u64 array_words;
+    u32 n1, n2, n3, log_n1, log_n2;
+    const u64 *t1;
+    u32 b0;  // first array of this launch (grid.y <= 65535)
+};
+
+// ntt1024_row_kernel<INV, W, false> for tiled shapes with an aligned destination: a warp loads its contiguous row,
+// the second 32-point step writes canonical words into the [1024 rows][4 word-columns] tile in TMA layout and one
+// thread sends it to dst viewed as [batch][1024][rows * W] with four box stores.
+template <bool INV, u32 W>
+__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks)
+    ntt1024_row_tma_kernel(const __grid_constant__ CUtensorMap dst_map, const RowTmaArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *tile = reinterpret_cast<u64 *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 tc_cta = blockIdx.x * kFastCols, b = a.b0 + blockIdx.y;
+    if (tid == 0) tma_prefetch_map(&dst_map);
+    const u32 tc = tc_cta + warp;
+    const u32 op = tc / W, c = tc - op * W;
+    const u32 i1 = op & (a.n1 - 1), r23 = op >> a.log_n1;
+    const u32 i2 = r23 & (a.n2 - 1), i3 = r23 >> a.log_n2;
+    const u32 rho = (i1 * a.n2 + i2) * a.n3 + i3;
+    const u64 *row = a.src + (u64)b * a.array_words + (u64)rho * (1024 * W) + c;
+    u64 v[32];
+#pragma unroll
+    for (int aa = 0; aa < 32; aa++) v[aa] = row[(32 * aa + lane) * W];
+    const u32 off0 = tma_tile_word(lane, warp);
+    dft1024_warp<INV, false, TF21_SHL_ROW, true, true>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane, tile + off0, 128u);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (u32 q = 0; q < 1024 / kTmaBoxRows; q++)
+            tma_store_3d(&dst_map, tc_cta, q * kTmaBoxRows, b, tile + q * kTmaBoxRows * kTmaTileCols);
+        tma_store_commit();
+        tma_store_wait_read();
+    }
+}
+
 struct SmallColArgs {
     const u64 *src;
     u64 *dst;
@@ -794,6 +839,11 @@ inline int get_tw_small(DeviceTables &t, int dev, unsigned log_b, unsigned log_n
 // TF21_NO_TMA=1 in the environment keeps the LDGSTS-staged column pass (A/B runs, tools/ab.sh)
 inline bool tma_disabled() {
     static const bool off = getenv("TF21_NO_TMA") != nullptr;
+    return off;
+}
+
+inline bool tma_row_disabled() {
+    static const bool off = getenv("TF21_NO_TMA") != nullptr || getenv("TF21_NO_TMA_ROW") != nullptr;
     return off;
 }
 
@@ -1179,6 +1229,28 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         grid = dim3((unsigned)g);
     }
     const bool has_post = post_scalar != 0 || post.lo != nullptr;
+    // tiled shapes without a post-scale and with an aligned destination send their output tiles by TMA
+    if (!has_post && a.n_tiles && !tma_row_disabled() && array_words < (1ull << 29)) {
+        CUtensorMap dst_map;
+        if (tma_encode_tile_map(&dst_map, dst, rows * w, batch)) {
+            RowTmaArgs ra{cur_src, array_words, a.n1, a.n2, a.n3, a.log_n1, a.log_n2, t1, 0};
+            for (u64 b0 = 0; b0 < batch; b0 += 65535) {
+                ra.b0 = (u32)b0;
+                const dim3 g2(a.n_tiles, (unsigned)(batch - b0 < 65535 ? batch - b0 : 65535));
+#define TF21_ROW_TMA_LAUNCH(I_, W_) \
+    TF21_LAUNCH_NAMED("ntt1024_row_tma_kernel", (ntt1024_row_tma_kernel<I_, W_>), g2, kFastThreads, kColTmaSmem, st, dst_map, ra)
+                if (w == 1) {
+                    if (inverse) TF21_ROW_TMA_LAUNCH(true, 1);
+                    else TF21_ROW_TMA_LAUNCH(false, 1);
+                } else {
+                    if (inverse) TF21_ROW_TMA_LAUNCH(true, 3);
+                    else TF21_ROW_TMA_LAUNCH(false, 3);
+                }
+#undef TF21_ROW_TMA_LAUNCH
+            }
+            return 0;
+        }
+    }
 #define TF21_ROW_LAUNCH(I_, W_, P_) \
     return launch_fast_named("ntt1024_row_kernel", (ntt1024_row_kernel<I_, W_, P_>), grid, a, st)
     if (w == 1) {

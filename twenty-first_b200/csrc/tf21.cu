@@ -67,6 +67,10 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
 #undef TF21_FAST_SMEM
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_tma_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_tma_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_tma_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
+        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_tma_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
         TF21_CUDA(cudaFuncSetAttribute(tma_tile_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTmaTileWords * 8 + 1024 + 16)));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
