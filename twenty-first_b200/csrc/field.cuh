@@ -442,8 +442,37 @@ __device__ __forceinline__ u64 gl_addp(u64 a, u64 t) {  // a any, t <= p -> any
         : "l"(a), "l"(t));
     return s;
 }
-__device__ __forceinline__ u64 gl_subp(u64 a, u64 t) {  // a any, t <= p -> any; both < p -> result < p
+#ifndef TF21_SUB_MADC
+#define TF21_SUB_MADC 1  /* high word of the borrow correction as IMAD.X (FMA pipe) instead of IADD3.X (ALU pipe) */
+#endif
+// an operand ptxas cannot fold (a __constant__ may be rewritten by the host): `one * 0xffffffff + hi + carry` stays a
+// multiply-add with carry-in, i.e. IMAD.X on the FMA-heavy pipe -- the butterfly-heavy kernels are ALU-pipe bound
+// (86 % against 55 %), so every addition that does not need a carry-OUT is worth moving
+__constant__ u32 c_gl_one = 1u;
+
+// `one`: a register holding 1 that ptxas cannot see through (kernels at the register limit load it once from global
+// memory -- the constant-bank default is re-read before every use)
+__device__ __forceinline__ u64 gl_subp(u64 a, u64 t, u32 one = c_gl_one) {  // a any, t <= p -> any; both < p -> result < p
     u64 s;
+#if TF21_SUB_MADC
+    asm("{\n\t.reg .u32 lo,hi,c,d,n0,n1; .reg .pred p;\n\t"
+        "not.b32 n0,%3;\n\t"
+        "not.b32 n1,%4;\n\t"
+        "add.cc.u32 d,0xffffffff,1;\n\t"
+        "addc.cc.u32 lo,%1,n0;\n\t"
+        "addc.cc.u32 hi,%2,n1;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.ne.u32 p,c,0;\n\t"          /* no carry = borrow: subtract EPS, i.e. (lo + 1, hi - 1 + carry) */
+        "@p bra GLSM%=;\n\t"
+        "add.cc.u32 lo,lo,1;\n\t"
+        "madc.lo.u32 hi,%5,0xffffffff,hi;\n\t"
+        "GLSM%=:\n\t"
+        "mov.b64 %0,{lo,hi};\n\t"
+        "}"
+        : "=l"(s)
+        : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)t), "r"((u32)(t >> 32)), "r"(one));
+    return s;
+#endif
     asm("{\n\t.reg .u32 lo,hi,c,d,n0,n1; .reg .pred p; .reg .u64 v;\n\t"
         "not.b32 n0,%3;\n\t"
         "not.b32 n1,%4;\n\t"
@@ -502,9 +531,9 @@ __device__ __forceinline__ u64 gl_canonp(u64 x) {  // any -> [0, p)
 
 // lazy sub for the butterflies: a any u64, t <= p -> any u64.  With TF21_SUB_WIDE the wrap correction
 // d - bw * EPS = (lo, hi - bw) + bw is one signed IMAD.WIDE (m * m + .., m = -bw) instead of two ALU ops.
-__device__ __forceinline__ u64 gl_subl(u64 a, u64 t) {
+__device__ __forceinline__ u64 gl_subl(u64 a, u64 t, u32 one = c_gl_one) {
 #if TF21_PRED_FIX
-    return gl_subp(a, t);
+    return gl_subp(a, t, one);
 #elif TF21_SUB_WIDE
     u32 lo, hi, m;
     asm("sub.cc.u32 %0,%3,%5;\n\tsubc.cc.u32 %1,%4,%6;\n\tsubc.u32 %2,0,0;"
@@ -548,7 +577,7 @@ __device__ __forceinline__ u64 gl_canonw(u64 x) {
 // (every shift twiddle of a 32- or 64-point transform: S is a multiple of 3).
 // z = x << (S % 32) as three 32-bit limbs, then fold by 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32.
 template <int S, int V = TF21_SHL_WIDE>
-__device__ __forceinline__ u64 gl_shlc(u64 x) {
+__device__ __forceinline__ u64 gl_shlc(u64 x, u32 one = c_gl_one) {
     static_assert(S > 0 && S < 96 && (S & 31) != 0, "shift twiddle out of range");
     constexpr int q = S >> 5, t = S & 31;
     const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
@@ -630,7 +659,7 @@ __device__ __forceinline__ u64 gl_shlc(u64 x) {
         const u32 c = (s < z0) ? 1u : 0u;
         const u64 T1 = gl_pack(0u - c, s);
         const u64 T2 = (u64)z1 + (u64)z2;
-        return gl_subl(T1, T2);
+        return gl_subl(T1, T2, one);
     } else {
         // z * 2^64 = z0 * EPS - (z2:z1):  z0 * EPS <= (2^32-1)^2 < p, (z2:z1) < 2^63
 #if TF21_SHL_CARRY
@@ -641,7 +670,7 @@ __device__ __forceinline__ u64 gl_shlc(u64 x) {
 #else
         const u64 a = (u64)z0 * GL_EPS;
 #endif
-        return gl_subl(a, gl_pack(z1, z2));
+        return gl_subl(a, gl_pack(z1, z2), one);
     }
 }
 

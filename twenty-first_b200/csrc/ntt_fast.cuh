@@ -91,12 +91,12 @@ __host__ __device__ constexpr u32 brev_bits(u32 k, int bits) {
 // array can never fall back to local memory (a `#pragma unroll` loop nest around inline asm with
 // labels was left partially rolled by the compiler for some sizes).
 template <bool INV, int A, int LS, int IDX, int SHLV>
-__device__ __forceinline__ void dft_pow2_step(u64 (&v)[1 << A]) {
+__device__ __forceinline__ void dft_pow2_step(u64 (&v)[1 << A], u32 one) {
     constexpr int N = 1 << A;
     if constexpr (LS > A) {
         return;
     } else if constexpr (IDX >= N / 2) {
-        dft_pow2_step<INV, A, LS + 1, 0, SHLV>(v);
+        dft_pow2_step<INV, A, LS + 1, 0, SHLV>(v, one);
     } else {
         constexpr int EU = (39 << (6 - A)) % 192;
         constexpr int m = 1 << LS, half = m >> 1;
@@ -108,27 +108,27 @@ __device__ __forceinline__ void dft_pow2_step(u64 (&v)[1 << A]) {
         constexpr int S = neg ? E - 96 : E;
         u64 t;
         if constexpr (S == 0) t = gl_canonw(v[ib]);
-        else t = gl_shlc<S, SHLV>(v[ib]);
+        else t = gl_shlc<S, SHLV>(v[ib], one);
         const u64 u = v[iu];
         if constexpr (!neg) {
             v[iu] = gl_addl(u, t);
-            v[ib] = gl_subl(u, t);
+            v[ib] = gl_subl(u, t, one);
         } else {
-            v[iu] = gl_subl(u, t);
+            v[iu] = gl_subl(u, t, one);
             v[ib] = gl_addl(u, t);
         }
-        dft_pow2_step<INV, A, LS, IDX + 1, SHLV>(v);
+        dft_pow2_step<INV, A, LS, IDX + 1, SHLV>(v, one);
     }
 }
 
 template <bool INV, int A, int SHLV = TF21_SHL_WIDE>
-__device__ __forceinline__ void dft_pow2(u64 (&v)[1 << A]) {
-    dft_pow2_step<INV, A, 1, 0, SHLV>(v);
+__device__ __forceinline__ void dft_pow2(u64 (&v)[1 << A], u32 one = c_gl_one) {
+    dft_pow2_step<INV, A, 1, 0, SHLV>(v, one);
 }
 
 template <bool INV, int SHLV = TF21_SHL_WIDE>
-__device__ __forceinline__ void dft32(u64 (&v)[32]) {
-    dft_pow2<INV, 5, SHLV>(v);
+__device__ __forceinline__ void dft32(u64 (&v)[32], u32 one = c_gl_one) {
+    dft_pow2<INV, 5, SHLV>(v, one);
 }
 
 // lazy twiddle from split tables (any u64 representative)
@@ -147,9 +147,11 @@ __device__ __forceinline__ u64 scale_factor_l(const ScaleTab &t, u64 idx) {
 template <bool INV, bool MASKMUL = false, int SHLV = TF21_SHL_WIDE, bool TILE_OUT = false, bool CANON_OUT = false>
 __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64 *tw0, const u64 *tw1, u32 lane,
                                              u64 *out1 = nullptr, u32 ss1 = 32u) {
+    // 1 in a register of its own: t1[0] = omega_1024^0 (see gl_subp); a global load is never re-issued by ptxas
+    const u32 one = (u32)__ldg(tw0 - lane);
 #pragma unroll 1
     for (int it = 0; it < 2; it++) {
-        dft32<INV, SHLV>(v);
+        dft32<INV, SHLV>(v, one);
         const u64 *tw = it ? tw1 : tw0;
         u64 *out = (TILE_OUT && it) ? out1 : slice + lane;
         const u32 ss = it ? (TILE_OUT ? ss1 : 32u) : kTransposeStride;
