@@ -325,7 +325,9 @@ constexpr size_t kColTmaSmem = kFastSmem + 1024 /* alignment slack */ + 16 /* mb
 // Same arithmetic as ntt1024_col_kernel<INV, true>; the tile travels by TMA.  Shared memory: one region that is
 // first the landing zone of the four box loads ([1024 rows][4 words], SWIZZLE_32B), then -- after every warp has
 // pulled its column into registers -- the four private transpose slices, and finally the outgoing tile.
-template <bool INV>
+// TW = false: the inter-pass twiddles are left to the load of the row pass (ntt1024_row_tma_kernel<.., true>: the
+// table omega_2^20^(i j) is symmetric, so the row pass reads it coalesced next to its data and both latencies overlap).
+template <bool INV, bool TW>
 __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks)
     ntt1024_col_tma_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map,
                            const ColTmaArgs a) {
@@ -359,7 +361,8 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks)
     for (int aa = 0; aa < 32; aa++) v[aa] = tile[off0 + 128 * aa];
     __syncthreads();  // the landing zone is dead: it becomes the private slices
     dft1024_warp<INV, TF21_COL_MASKMUL, TF21_SHL_COL, true>(v, tile + warp * kFastS, a.t1 + lane,
-                                                            a.tw_full + jrest * 1024 + lane, lane, tile + off0, 128u);
+                                                            TW ? a.tw_full + jrest * 1024 + lane : nullptr, lane,
+                                                            tile + off0, 128u);
     fence_proxy_async_smem();  // my generic-proxy writes of the outgoing tile -> visible to the TMA engine
     __syncthreads();
     if (tid == 0) {
@@ -503,12 +506,13 @@ struct RowTmaArgs {
     u32 n1, n2, n3, log_n1, log_n2;
     const u64 *t1;
     u32 b0;  // first array of this launch (grid.y <= 65535)
+    const u64 *tw_in;  // TWIN: [1024][1024] inter-pass twiddles of the preceding column pass, applied on load
 };
 
 // ntt1024_row_kernel<INV, W, false> for tiled shapes with an aligned destination: a warp loads its contiguous row,
 // the second 32-point step writes canonical words into the [1024 rows][4 word-columns] tile in TMA layout and one
 // thread sends it to dst viewed as [batch][1024][rows * W] with four box stores.
-template <bool INV, u32 W>
+template <bool INV, u32 W, bool TWIN>
 __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks)
     ntt1024_row_tma_kernel(const __grid_constant__ CUtensorMap dst_map, const RowTmaArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -523,8 +527,16 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks)
     const u32 rho = (i1 * a.n2 + i2) * a.n3 + i3;
     const u64 *row = a.src + (u64)b * a.array_words + (u64)rho * (1024 * W) + c;
     u64 v[32];
+    if constexpr (TWIN) {
+        // element j of row rho of a 2^20-point block carries omega^(i j) with i = rho mod 1024 (the column-pass digit
+        // is the last leading digit); T[i][j] = T[j][i]
+        const u64 *twr = a.tw_in + (u64)(rho & 1023u) * 1024 + lane;
 #pragma unroll
-    for (int aa = 0; aa < 32; aa++) v[aa] = row[(32 * aa + lane) * W];
+        for (int aa = 0; aa < 32; aa++) v[aa] = gl_mul(row[(32 * aa + lane) * W], __ldg(twr + 32 * aa));
+    } else {
+#pragma unroll
+        for (int aa = 0; aa < 32; aa++) v[aa] = row[(32 * aa + lane) * W];
+    }
     const u32 off0 = tma_tile_word(lane, warp);
     dft1024_warp<INV, false, TF21_SHL_ROW, true, true>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane, tile + off0, 128u);
     fence_proxy_async_smem();
@@ -844,6 +856,15 @@ inline bool tma_disabled() {
     return off;
 }
 
+// the unscale factor of an inverse transform is folded into the first twiddle table whenever there is a leading pass
+inline bool post_scalar_is_foldable(u64 post_scalar, u32 n_lead) { return post_scalar == 0 || n_lead > 0; }
+// Measured (2^20 x256): with the inter-pass twiddles applied on the load of the row pass the column pass drops
+// 1.32 -> 1.08 ms but the row pass grows 1.10 -> 1.43 ms (the 32 extra products sit in front of the first butterflies,
+// where all 32 elements are live) -- 2.52 ms against 2.42 ms, so the deferral stays off unless TF21_TW_DEFER is set.
+inline bool tma_defer_disabled() {
+    static const bool off = getenv("TF21_TW_DEFER") == nullptr;
+    return off;
+}
 inline bool tma_row_disabled() {
     static const bool off = getenv("TF21_NO_TMA") != nullptr || getenv("TF21_NO_TMA_ROW") != nullptr;
     return off;
@@ -1083,6 +1104,11 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     u64 cur_n_in = n_in;
     ScaleTab cur_pre = pre;
     u32 consumed = 0;
+    // will the last pass take the TMA-store form?  (then it can also apply the inter-pass twiddles of a TMA column pass)
+    const bool row_tma_ok = post_scalar_is_foldable(post_scalar, n_lead) && post.lo == nullptr && !tma_row_disabled() &&
+                            ((n >> 10) * w) % kFastCols == 0 && array_words < (1ull << 29) && ((uintptr_t)dst & 15) == 0 &&
+                            tma_encoder() != nullptr;
+    const u64 *deferred_tw = nullptr;
     for (u32 p = 0; p < n_lead; p++) {
         const u32 lp = lead[p];
         const u32 log_inner = log_n - consumed - lp;
@@ -1138,16 +1164,23 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
                 if (tma_encode_tile_map(&src_map, cur_src, inner_words, slabs) &&
                     tma_encode_tile_map(&dst_map, scratch, inner_words, slabs)) {
                     ColTmaArgs ta{t1, tw_full, w, 0};
+                    const bool defer = row_tma_ok && log_b == 20 && !tma_defer_disabled();
+                    if (defer) deferred_tw = tw_full;
                     for (u64 s0 = 0; s0 < slabs; s0 += 65535) {
                         ta.slab0 = (u32)s0;
                         const dim3 grid((unsigned)(inner_words / kTmaTileCols),
                                         (unsigned)(slabs - s0 < 65535 ? slabs - s0 : 65535));
-                        if (inverse)
-                            TF21_LAUNCH_NAMED("ntt1024_col_tma_kernel<true>", (ntt1024_col_tma_kernel<true>), grid,
-                                              kFastThreads, kColTmaSmem, st, src_map, dst_map, ta);
-                        else
-                            TF21_LAUNCH_NAMED("ntt1024_col_tma_kernel<false>", (ntt1024_col_tma_kernel<false>), grid,
-                                              kFastThreads, kColTmaSmem, st, src_map, dst_map, ta);
+#define TF21_COL_TMA_LAUNCH(I_, T_)                                                                                      \
+    TF21_LAUNCH_NAMED("ntt1024_col_tma_kernel<" #I_ ">", (ntt1024_col_tma_kernel<I_, T_>), grid, kFastThreads, kColTmaSmem, \
+                      st, src_map, dst_map, ta)
+                        if (inverse) {
+                            if (defer) TF21_COL_TMA_LAUNCH(true, false);
+                            else TF21_COL_TMA_LAUNCH(true, true);
+                        } else {
+                            if (defer) TF21_COL_TMA_LAUNCH(false, false);
+                            else TF21_COL_TMA_LAUNCH(false, true);
+                        }
+#undef TF21_COL_TMA_LAUNCH
                     }
                     consumed += lp;
                     cur_src = scratch;
@@ -1235,12 +1268,19 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     if (!has_post && a.n_tiles && !tma_row_disabled() && array_words < (1ull << 29)) {
         CUtensorMap dst_map;
         if (tma_encode_tile_map(&dst_map, dst, rows * w, batch)) {
-            RowTmaArgs ra{cur_src, array_words, a.n1, a.n2, a.n3, a.log_n1, a.log_n2, t1, 0};
+            RowTmaArgs ra{cur_src, array_words, a.n1, a.n2, a.n3, a.log_n1, a.log_n2, t1, 0, deferred_tw};
             for (u64 b0 = 0; b0 < batch; b0 += 65535) {
                 ra.b0 = (u32)b0;
                 const dim3 g2(a.n_tiles, (unsigned)(batch - b0 < 65535 ? batch - b0 : 65535));
-#define TF21_ROW_TMA_LAUNCH(I_, W_) \
-    TF21_LAUNCH_NAMED("ntt1024_row_tma_kernel", (ntt1024_row_tma_kernel<I_, W_>), g2, kFastThreads, kColTmaSmem, st, dst_map, ra)
+#define TF21_ROW_TMA_LAUNCH(I_, W_)                                                                                      \
+    do {                                                                                                                \
+        if (deferred_tw)                                                                                                \
+            TF21_LAUNCH_NAMED("ntt1024_row_tma_kernel", (ntt1024_row_tma_kernel<I_, W_, true>), g2, kFastThreads,       \
+                              kColTmaSmem, st, dst_map, ra);                                                            \
+        else                                                                                                            \
+            TF21_LAUNCH_NAMED("ntt1024_row_tma_kernel", (ntt1024_row_tma_kernel<I_, W_, false>), g2, kFastThreads,      \
+                              kColTmaSmem, st, dst_map, ra);                                                            \
+    } while (0)
                 if (w == 1) {
                     if (inverse) TF21_ROW_TMA_LAUNCH(true, 1);
                     else TF21_ROW_TMA_LAUNCH(false, 1);
@@ -1252,6 +1292,10 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
             }
             return 0;
         }
+    }
+    if (deferred_tw) {  // unreachable by construction of row_tma_ok; never return an untwiddled transform
+        snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "internal: deferred twiddles without a TMA row pass");
+        return TF21_E_CUDA;
     }
 #define TF21_ROW_LAUNCH(I_, W_, P_) \
     return launch_fast_named("ntt1024_row_kernel", (ntt1024_row_kernel<I_, W_, P_>), grid, a, st)

@@ -65,12 +65,20 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
         TF21_FAST_SMEM((ntt1024_row_kernel<true, 3, false>));
         TF21_FAST_SMEM((ntt1024_row_kernel<true, 3, true>));
 #undef TF21_FAST_SMEM
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_col_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_tma_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_tma_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_tma_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
-        TF21_CUDA(cudaFuncSetAttribute(ntt1024_row_tma_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem));
+#define TF21_TMA_SMEM(K) TF21_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem))
+        TF21_TMA_SMEM((ntt1024_col_tma_kernel<false, false>));
+        TF21_TMA_SMEM((ntt1024_col_tma_kernel<false, true>));
+        TF21_TMA_SMEM((ntt1024_col_tma_kernel<true, false>));
+        TF21_TMA_SMEM((ntt1024_col_tma_kernel<true, true>));
+        TF21_TMA_SMEM((ntt1024_row_tma_kernel<false, 1, true>));
+        TF21_TMA_SMEM((ntt1024_row_tma_kernel<true, 1, true>));
+        TF21_TMA_SMEM((ntt1024_row_tma_kernel<false, 3, true>));
+        TF21_TMA_SMEM((ntt1024_row_tma_kernel<true, 3, true>));
+        TF21_TMA_SMEM((ntt1024_row_tma_kernel<false, 1, false>));
+        TF21_TMA_SMEM((ntt1024_row_tma_kernel<true, 1, false>));
+        TF21_TMA_SMEM((ntt1024_row_tma_kernel<false, 3, false>));
+        TF21_TMA_SMEM((ntt1024_row_tma_kernel<true, 3, false>));
+#undef TF21_TMA_SMEM
         TF21_CUDA(cudaFuncSetAttribute(tma_tile_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTmaTileWords * 8 + 1024 + 16)));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_CUDA(cudaFuncSetAttribute(ntt1024_single_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
