@@ -82,3 +82,15 @@ def test_header_is_plain_c(tmp_path):
     inc = os.path.join(ROOT, "include")
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", f"-I{inc}", str(src)],
                    check=True)
+
+
+def test_rust_sys_crate_declares_exactly_the_header():
+    """host/rust/tf21-sys/src/lib.rs is generated from include/tf21.h + the ctypes table (tools/gen_rust_sys.py);
+    the committed file must be up to date, so the Rust shim binds what the library exports"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "tools", "gen_rust_sys.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(ROOT, "host", "rust", "tf21-sys", "src", "lib.rs")) as f:
+        assert f.read() == mod.generate()

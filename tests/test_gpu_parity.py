@@ -922,3 +922,26 @@ def test_tma_tile_layout_matches_the_swizzle_formula(tf):
         want = np.zeros(4096, dtype=np.int64)
         want[idx.reshape(-1)] = (r * inner + 4 * t + c).reshape(-1)
         assert np.array_equal(got[t], want), t
+
+
+@pytest.mark.parametrize("width", [1, 3])
+@pytest.mark.parametrize("log2n", list(range(1, 10)))
+def test_small_n_register_kernel(tf, oracle, log2n, width):
+    """n < 2^10 (reference benches at 2^7, benches/ntt.rs:19): a warp takes 1024 consecutive elements = whole
+    columns; batches that do not fill the last 1024-element chunk, forward and inverse, on the device path"""
+    import torch
+
+    dev = importlib.import_module("twenty-first_b200.device")
+    n = 1 << log2n
+    for batch in (1, 3, (1024 >> log2n), (1024 >> log2n) + 1, 777):
+        x = rnd(0x5A00 + 16 * log2n + width + batch, n * width * batch)
+        x[: min(x.size, 4)] = [P - 1, 0, 0xFFFFFFFF00000000, 1][: min(x.size, 4)]
+        want = x.copy()
+        assert oracle.ntt_batch(want, n, width, batch, False) == 0
+        d = torch.from_numpy(x.view(np.int64)).cuda()
+        dev.ntt_(d, n, width, False)
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy().view(np.uint64), want), (log2n, width, batch)
+        dev.ntt_(d, n, width, True)
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy().view(np.uint64), x), (log2n, width, batch)

@@ -131,6 +131,46 @@ __device__ __forceinline__ void dft32(u64 (&v)[32], u32 one = c_gl_one) {
     dft_pow2<INV, 5, SHLV>(v, one);
 }
 
+// the same butterflies on the 2^A consecutive registers v[OFF .. OFF + 2^A) of a 32-register column
+template <bool INV, int A, int OFF, int LS, int IDX, int SHLV>
+__device__ __forceinline__ void dft_sub_step(u64 (&v)[32], u32 one) {
+    constexpr int N = 1 << A;
+    if constexpr (LS > A) {
+        return;
+    } else if constexpr (IDX >= N / 2) {
+        dft_sub_step<INV, A, OFF, LS + 1, 0, SHLV>(v, one);
+    } else {
+        constexpr int EU = (39 << (6 - A)) % 192;
+        constexpr int m = 1 << LS, half = m >> 1;
+        constexpr int k = (IDX / half) * m, j = IDX % half;
+        constexpr int iu = OFF + brev_bits(k + j, A), ib = OFF + brev_bits(k + j + half, A);
+        constexpr int E0 = (EU * j * (N / m)) % 192;
+        constexpr int E = INV ? (192 - E0) % 192 : E0;
+        constexpr bool neg = E >= 96;
+        constexpr int S = neg ? E - 96 : E;
+        u64 t;
+        if constexpr (S == 0) t = gl_canonw(v[ib]);
+        else t = gl_shlc<S, SHLV>(v[ib], one);
+        const u64 u = v[iu];
+        if constexpr (!neg) {
+            v[iu] = gl_addl(u, t);
+            v[ib] = gl_subl(u, t, one);
+        } else {
+            v[iu] = gl_subl(u, t, one);
+            v[ib] = gl_addl(u, t);
+        }
+        dft_sub_step<INV, A, OFF, LS, IDX + 1, SHLV>(v, one);
+    }
+}
+// 32 / 2^A independent 2^A-point DFTs on the register groups v[g 2^A .. (g + 1) 2^A); out: v[g 2^A + brev_A(k)]
+template <bool INV, int A, int G = 0>
+__device__ __forceinline__ void dft_groups(u64 (&v)[32], u32 one) {
+    if constexpr (A > 0 && G < (32 >> A)) {
+        dft_sub_step<INV, A, G << A, 1, 0, TF21_SHL_WIDE>(v, one);
+        dft_groups<INV, A, G + 1>(v, one);
+    }
+}
+
 // lazy twiddle from split tables (any u64 representative)
 __device__ __forceinline__ u64 scale_factor_l(const ScaleTab &t, u64 idx) {
     return gl_mul(__ldg(t.lo + (idx & ((1ull << t.h) - 1))), __ldg(t.hi + (idx >> t.h)));
@@ -616,64 +656,20 @@ __global__ void __launch_bounds__(128) ntt_small_col_kernel(const SmallColArgs a
     }
 }
 
-// shift-twiddled inputs of one output group d of the pruned pass: z[r] = x[r] * w^(r d)
-template <int A, int LNZ, int D, int R>
-__device__ __forceinline__ void pruned_twiddle(const u64 (&x)[1 << LNZ], u64 (&z)[1 << LNZ]) {
-    if constexpr (R < (1 << LNZ)) {
-        constexpr int EU = (39 << (6 - A)) % 192;
-        constexpr int E = (EU * R * D) % 192;
-        constexpr bool neg = E >= 96;
-        constexpr int S = neg ? E - 96 : E;
-        u64 t;
-        if constexpr (S == 0) t = x[R];
-        else t = gl_shlc<S>(x[R]);
-        if constexpr (neg) t = gl_subl(0ull, gl_canonw(t));
-        z[R] = t;
-        pruned_twiddle<A, LNZ, D, R + 1>(x, z);
-    }
-}
-
-template <int A, int LNZ, int D, int C>
-__device__ __forceinline__ void pruned_store(u64 (&z)[1 << LNZ], u64 *dst, const u64 *tcol, u64 inner_elems,
-                                             u64 inner_words, u64 &tc, u64 gM) {
-    if constexpr (C < (1 << LNZ)) {
-        constexpr int M = (1 << A) >> LNZ;
-        constexpr int i = M * C + D;
-        u64 v = z[brev_bits(C, LNZ)];
-        if (tcol) {
-            v = gl_mul(v, __ldg(tcol + (u64)i * inner_elems));
-        } else {
-            if constexpr (i != 0) v = gl_mul(v, tc);
-            if constexpr (C + 1 < (1 << LNZ)) tc = gl_mul(tc, gM);
-        }
-        dst[(u64)i * inner_words] = v;
-        pruned_store<A, LNZ, D, C + 1>(z, dst, tcol, inner_elems, inner_words, tc, gM);
-    }
-}
-
-template <int A, int LNZ, int D>
-__device__ __forceinline__ void pruned_steps(const u64 (&x)[1 << LNZ], u64 *dst, const u64 *tcol, u64 inner_elems,
-                                             u64 inner_words, u64 g, u64 gM, u64 gd) {
-    constexpr int M = (1 << A) >> LNZ;
-    if constexpr (D < M) {
-        u64 z[1 << LNZ];
-        pruned_twiddle<A, LNZ, D, 0>(x, z);
-        dft_pow2<false, LNZ>(z);
-        u64 tc = gd;
-        pruned_store<A, LNZ, D, 0>(z, dst, tcol, inner_elems, inner_words, tc, gM);
-        if (!tcol) gd = gl_mul(gd, g);
-        pruned_steps<A, LNZ, D + 1>(x, dst, tcol, inner_elems, inner_words, g, gM, gd);
-    }
-}
+// omega_64^k, k < 64 (canonical; = +-2^(39 k mod 96)), filled by get_tables: the twiddles of the pruned pass below,
+// read with a warp-uniform index (constant-bank broadcast)
+__constant__ u64 c_w64[64];
 
 // Pruned column pass for zero-extended inputs (the `resize(order, ZERO)` of fast_coset_evaluate,
 // polynomial.rs:1396-1397): only the first NZ = 2^LNZ rows of a 2^A-point column can be non-zero, so
 // with M = 2^A / NZ and k = M c + d:  X[M c + d] = sum_{a < NZ} (x_a w^(a d)) w_NZ^(a c)  -- for every d one
-// NZ-point DFT of shift-twiddled inputs.  Reads NZ rows, writes 2^A rows, keeps 2 NZ values live.
+// NZ-point DFT of twiddled inputs.  Reads NZ rows, writes 2^A rows, keeps 2 NZ values live.
+// The loop over d stays ROLLED: unrolled (shift twiddles as immediates) the 64-point form is 74 KB of
+// straight-line code and ran at 6.9 `no_instruction` stalls per issue (profiles/r02d_ncu_lde26_summary.txt);
+// the twiddles w^(a d) are now general products with a warp-uniform table entry.
 template <int A, int LNZ>
 __global__ void __launch_bounds__(128) ntt_small_col_pruned_kernel(const SmallColArgs a) {
     constexpr int NP = 1 << A, NZ = 1 << LNZ, M = NP / NZ;
-    constexpr int EU = (39 << (6 - A)) % 192;
     const u64 gid = (u64)blockIdx.x * 128 + threadIdx.x;
     const u64 q = gid % a.inner_words;
     const u64 rest = gid / a.inner_words;
@@ -704,7 +700,28 @@ __global__ void __launch_bounds__(128) ntt_small_col_pruned_kernel(const SmallCo
 #pragma unroll
         for (int k = 0; k < A - LNZ; k++) gM = gl_mul(gM, gM);
     }
-    pruned_steps<A, LNZ, 0>(x, dst, tcol, inner_elems, a.inner_words, g, gM, gd);
+#pragma unroll 1
+    for (int d = 0; d < M; d++) {
+        u64 z[NZ];
+        z[0] = x[0];
+#pragma unroll
+        for (int r = 1; r < NZ; r++) z[r] = gl_mul(x[r], c_w64[((r * d) & (NP - 1)) * (64 / NP)]);
+        dft_pow2<false, LNZ>(z);
+        u64 tc = gd;
+#pragma unroll
+        for (int c = 0; c < NZ; c++) {
+            const int i = M * c + d;
+            u64 v = z[brev_bits(c, LNZ)];
+            if (tcol) {
+                v = gl_mul(v, __ldg(tcol + (u64)i * inner_elems));
+            } else {
+                v = gl_mul(v, tc);  // i == 0: tc = 1 (or the folded scalar)
+                if (c + 1 < NZ) tc = gl_mul(tc, gM);
+            }
+            dst[(u64)i * a.inner_words] = v;
+        }
+        if (!tcol) gd = gl_mul(gd, g);
+    }
 }
 
 struct FastSingleArgs {
@@ -754,6 +771,92 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_single_k
 }
 
 
+// ---- n = 2^K < 1024: a warp takes 1024 consecutive elements = 2^(10-K) whole columns, all in registers ------
+// (reference benches at 2^7, benches/ntt.rs:19).  Flat element J of the batch = (array J / n, index J % n); a warp
+// owns J0 .. J0 + 1023 of one coefficient lane (w = 3: the three warps of a chunk interleave like the 2^10 kernel).
+//   K > 5: step A = 2^(K-5)-point DFTs over the low bits of the register index, twiddle omega_n^(k1 lane), 32 x 32
+//          transpose, step B = 32-point DFT: X[k1 + 2^(K-5) k2] of column c sits in lane (c, k1), register k2;
+//   K <= 5: transpose first, then 2^(5-K) independent 2^K-point DFTs on register groups (no general product).
+struct SmallNArgs {
+    const u64 *src;
+    u64 *dst;
+    u64 total_elems;   // batch * n
+    const u64 *tw;     // K > 5: [2^(K-5)][32] scalar * omega_n^(+-k1 b); else nullptr
+    u64 post_scalar;   // K <= 5: n^-1 applied on store (0 = none)
+    u32 w;
+    u32 scaled;        // K > 5: the table carries a scalar other than one (row 0 is not all ones)
+};
+
+template <bool INV, int K>
+__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt_small_n_kernel(const SmallNArgs a) {
+    static_assert(K >= 1 && K <= 9, "sizes below 2^10");
+    extern __shared__ __align__(16) u64 smem[];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 g = (u64)blockIdx.x * kFastCols + warp;  // (chunk, coefficient lane)
+    const u64 chunk = g / a.w;
+    const u32 c = (u32)(g - chunk * a.w);
+    const u64 j0 = chunk * 1024;
+    if (j0 >= a.total_elems) return;
+    const u64 left = a.total_elems - j0;  // a multiple of n; < 1024 only in the last chunk
+    const u64 *src = a.src + j0 * a.w + c;
+    u64 *slice = smem + warp * kFastS;
+    const u32 one = c_gl_one;
+    u64 v[32];
+#pragma unroll
+    for (int aa = 0; aa < 32; aa++) {
+        const u32 j = 32 * aa + lane;
+        v[aa] = j < left ? src[(u64)j * a.w] : 0ull;
+    }
+    u32 base;  // position of register 0 of this lane in the chunk after the last step; register k2 adds k2 * stride
+    constexpr u32 stride = K > 5 ? (1u << (K - 5)) : 1u;
+    if constexpr (K > 5) {
+        constexpr int AP = K - 5;
+        dft_groups<INV, AP>(v, one);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const int grp = r >> AP, k1 = r & ((1 << AP) - 1);
+            const int reg = (grp << AP) + (int)brev_bits((u32)k1, AP);
+            u64 x = v[reg];
+            if (k1 != 0 || a.scaled) x = gl_mul(x, __ldg(a.tw + k1 * 32 + lane));  // unscaled row 0 is all ones
+            slice[r * kTransposeStride + lane] = x;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < 32; b++) v[b] = slice[lane * kTransposeStride + b];
+        dft_groups<INV, 5>(v, one);
+        base = ((lane >> AP) << K) + (lane & ((1u << AP) - 1));
+    } else {
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; r++) slice[r * kTransposeStride + lane] = v[r];
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < 32; b++) v[b] = slice[lane * kTransposeStride + b];
+        dft_groups<INV, K>(v, one);
+        base = 32 * lane;
+    }
+    __syncwarp();
+    // natural order into the slice, then coalesced stores
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+        // K > 5: register brev5(k2) holds X[.. + stride * k2]; K <= 5: register (grp << K) + brev_K(k) holds X[grp][k]
+        const int reg = K > 5 ? (int)brev5((u32)r) : ((r >> K) << K) + (int)brev_bits((u32)(r & ((1 << K) - 1)), K);
+        slice[base + (u32)r * stride] = v[reg];
+    }
+    __syncwarp();
+    u64 *dst = a.dst + j0 * a.w + c;
+#pragma unroll 8
+    for (int aa = 0; aa < 32; aa++) {
+        const u32 j = 32 * aa + lane;
+        if (j < left) {
+            u64 x = slice[j];
+            if (K <= 5 && a.post_scalar) x = gl_mul(x, a.post_scalar);
+            dst[(u64)j * a.w] = gl_canonw(x);
+        }
+    }
+}
+
 // ---- tables for the fast path ---------------------------------------------------------------------
 struct FastTables {
     std::map<int, u64 *> t1;                                             // inverse -> [32][32]
@@ -761,6 +864,33 @@ struct FastTables {
     std::map<std::tuple<unsigned, unsigned, int, u64>, u64 *> tw_small;  // same key, [N_p][B / N_p] layout
 };
 static std::map<int, FastTables> g_fast_tables;  // by device, guarded by g_mutex
+static std::map<std::tuple<int, unsigned, int, u64>, u64 *> g_small_n_tw;  // (device, K, inverse, scalar), guarded by g_mutex
+
+// [2^(K-5)][32] scalar * omega_{2^K}^(+-k1 b) for the 2^K-point kernel, 5 < K < 10
+inline int get_small_n_tw(DeviceTables &t, int dev, unsigned k, int inverse, u64 scalar, const u64 **out) {
+    auto key = std::make_tuple(dev, k, inverse, scalar);
+    auto it = g_small_n_tw.find(key);
+    if (it != g_small_n_tw.end()) {
+        *out = it->second;
+        return 0;
+    }
+    u64 w = hgl_root_of_unity(k);
+    if (inverse) w = hgl_inv(w);
+    const u32 rows = 1u << (k - 5);
+    std::vector<u64> h(rows * 32);
+    for (u32 k1 = 0; k1 < rows; k1++) {
+        u64 step = hgl_pow(w, k1), acc = scalar % GL_P;
+        for (u32 b = 0; b < 32; b++) {
+            h[k1 * 32 + b] = acc;
+            acc = hgl_mul(acc, step);
+        }
+    }
+    u64 *d;
+    TF21_TRY(upload(t, h, &d));
+    g_small_n_tw[key] = d;
+    *out = d;
+    return 0;
+}
 
 inline int get_t1(DeviceTables &t, int dev, int inverse, const u64 **out) {
     FastTables &ft = g_fast_tables[dev];
@@ -863,6 +993,10 @@ inline bool post_scalar_is_foldable(u64 post_scalar, u32 n_lead) { return post_s
 // where all 32 elements are live) -- 2.52 ms against 2.42 ms, so the deferral stays off unless TF21_TW_DEFER is set.
 inline bool tma_defer_disabled() {
     static const bool off = getenv("TF21_TW_DEFER") == nullptr;
+    return off;
+}
+inline bool small_n_disabled() {
+    static const bool off = getenv("TF21_NO_SMALL_N") != nullptr;
     return off;
 }
 inline bool tma_row_disabled() {
@@ -1043,8 +1177,41 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
                    int inverse, ScaleTab pre, ScaleTab post, u64 post_scalar, u64 *scratch, cudaStream_t st) {
     const u32 log_n = ilog2_u64(n);
     const u64 array_words = n * w;
-    if (log_n < 10)
+    if (log_n < 10) {
+        // plain transforms (no zero extension, no coset scale tables) of whole columns: the register kernel
+        if (n_in == n && !pre.lo && !post.lo && !small_n_disabled()) {
+            SmallNArgs a{};
+            a.src = src;
+            a.dst = dst;
+            a.total_elems = batch * n;
+            a.w = w;
+            if (log_n > 5) {
+                std::lock_guard<std::mutex> lock(g_mutex);
+                TF21_TRY(get_small_n_tw(tabs, dev, log_n, inverse, post_scalar ? post_scalar : 1, &a.tw));
+                a.scaled = (post_scalar != 0 && post_scalar % GL_P != 1) ? 1u : 0u;
+            } else {
+                a.post_scalar = post_scalar;
+            }
+            const u64 chunks = (a.total_elems + 1023) / 1024;
+            const u64 grid = (chunks * w + kFastCols - 1) / kFastCols;
+            if (grid > 0x7fffffffull) return TF21_E_LEN_TOO_LARGE;
+#define TF21_SMALL_N_CASE(K_)                                                                                       \
+    case K_:                                                                                                       \
+        if (inverse)                                                                                               \
+            TF21_LAUNCH_NAMED("ntt_small_n_kernel", (ntt_small_n_kernel<true, K_>), (unsigned)grid, kFastThreads,   \
+                              kFastSmem, st, a);                                                                   \
+        else                                                                                                       \
+            TF21_LAUNCH_NAMED("ntt_small_n_kernel", (ntt_small_n_kernel<false, K_>), (unsigned)grid, kFastThreads,  \
+                              kFastSmem, st, a);                                                                   \
+        return 0;
+            switch (log_n) {
+                TF21_SMALL_N_CASE(1) TF21_SMALL_N_CASE(2) TF21_SMALL_N_CASE(3) TF21_SMALL_N_CASE(4) TF21_SMALL_N_CASE(5)
+                TF21_SMALL_N_CASE(6) TF21_SMALL_N_CASE(7) TF21_SMALL_N_CASE(8) TF21_SMALL_N_CASE(9)
+            }
+#undef TF21_SMALL_N_CASE
+        }
         return ntt_run_generic(tabs, src, n_in, dst, n, w, batch, inverse, pre, post, post_scalar, scratch, st);
+    }
 
     const u64 *t1 = nullptr;
     {

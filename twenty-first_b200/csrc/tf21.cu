@@ -33,6 +33,13 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
             TF21_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         }
         TF21_TRY(upload_tip5_constants());
+        {
+            u64 w64[64];
+            const u64 w = hgl_root_of_unity(6);
+            for (int k = 0; k < 64; k++) w64[k] = hgl_pow(w, k);
+            TF21_CUDA(cudaMemcpyToSymbol(c_w64, w64, sizeof(w64)));
+            TF21_CUDA(cudaStreamSynchronize(nullptr));
+        }
         for (int inv = 0; inv < 2; inv++) {
             std::vector<u64> tw((1u << kNttMaxLogPass) - 1);
             for (u32 l = 1; l <= kNttMaxLogPass; l++) {
@@ -65,6 +72,12 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
         TF21_FAST_SMEM((ntt1024_row_kernel<true, 3, false>));
         TF21_FAST_SMEM((ntt1024_row_kernel<true, 3, true>));
 #undef TF21_FAST_SMEM
+#define TF21_SMALL_N_SMEM(K_)                                                                                          \
+    TF21_CUDA(cudaFuncSetAttribute(ntt_small_n_kernel<false, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem)); \
+    TF21_CUDA(cudaFuncSetAttribute(ntt_small_n_kernel<true, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+        TF21_SMALL_N_SMEM(1) TF21_SMALL_N_SMEM(2) TF21_SMALL_N_SMEM(3) TF21_SMALL_N_SMEM(4) TF21_SMALL_N_SMEM(5)
+        TF21_SMALL_N_SMEM(6) TF21_SMALL_N_SMEM(7) TF21_SMALL_N_SMEM(8) TF21_SMALL_N_SMEM(9)
+#undef TF21_SMALL_N_SMEM
 #define TF21_TMA_SMEM(K) TF21_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColTmaSmem))
         TF21_TMA_SMEM((ntt1024_col_tma_kernel<false, false>));
         TF21_TMA_SMEM((ntt1024_col_tma_kernel<false, true>));
@@ -261,6 +274,7 @@ int tf21_shutdown(void) {
     }
     g_devices.clear();
     g_fast_tables.clear();  // their device pointers lived in `owned` and are gone: never hand them out again
+    g_small_n_tw.clear();
     if (prev >= 0) cudaSetDevice(prev);
     return 0;
 }
