@@ -8,7 +8,14 @@ dev.init(0)
 cuda = torch.device("cuda:0")
 what = sys.argv[1] if len(sys.argv) > 1 else "ntt20"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-if what == "ntt20":
+if what.startswith("ntt:"):  # ntt:<log2n>:<batch>[:<width>]
+    parts = what.split(":")
+    l2, batch = int(parts[1]), int(parts[2])
+    w = int(parts[3]) if len(parts) > 3 else 1
+    x = torch.randint(0, 2**63 - 1, ((batch * w) << l2,), dtype=torch.int64, device=cuda)
+    for _ in range(reps):
+        dev.ntt_(x, 1 << l2, w, False)
+elif what == "ntt20":
     cols = int(os.environ.get("COLS", "64"))
     x = torch.randint(0, 2**63 - 1, (cols << 20,), dtype=torch.int64, device=cuda)
     for _ in range(reps):

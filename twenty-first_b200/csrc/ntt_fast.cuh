@@ -132,18 +132,18 @@ __device__ __forceinline__ void dft32(u64 (&v)[32], u32 one = c_gl_one) {
 }
 
 // the same butterflies on the 2^A consecutive registers v[OFF .. OFF + 2^A) of a 32-register column
-template <bool INV, int A, int OFF, int LS, int IDX, int SHLV>
+template <bool INV, int A, int OFF, int LS, int IDX, int SHLV, int STRIDE = 1>
 __device__ __forceinline__ void dft_sub_step(u64 (&v)[32], u32 one) {
     constexpr int N = 1 << A;
     if constexpr (LS > A) {
         return;
     } else if constexpr (IDX >= N / 2) {
-        dft_sub_step<INV, A, OFF, LS + 1, 0, SHLV>(v, one);
+        dft_sub_step<INV, A, OFF, LS + 1, 0, SHLV, STRIDE>(v, one);
     } else {
         constexpr int EU = (39 << (6 - A)) % 192;
         constexpr int m = 1 << LS, half = m >> 1;
         constexpr int k = (IDX / half) * m, j = IDX % half;
-        constexpr int iu = OFF + brev_bits(k + j, A), ib = OFF + brev_bits(k + j + half, A);
+        constexpr int iu = OFF + STRIDE * brev_bits(k + j, A), ib = OFF + STRIDE * brev_bits(k + j + half, A);
         constexpr int E0 = (EU * j * (N / m)) % 192;
         constexpr int E = INV ? (192 - E0) % 192 : E0;
         constexpr bool neg = E >= 96;
@@ -159,7 +159,16 @@ __device__ __forceinline__ void dft_sub_step(u64 (&v)[32], u32 one) {
             v[iu] = gl_subl(u, t, one);
             v[ib] = gl_addl(u, t);
         }
-        dft_sub_step<INV, A, OFF, LS, IDX + 1, SHLV>(v, one);
+        dft_sub_step<INV, A, OFF, LS, IDX + 1, SHLV, STRIDE>(v, one);
+    }
+}
+// 32 / 2^A independent 2^A-point DFTs on the STRIDED register groups v[o + s 2^(5-A)], s < 2^A, o < 2^(5-A)
+// (the DFT runs over the HIGH bits of the register index); out: v[o + brev_A(k) 2^(5-A)]
+template <bool INV, int A, int O = 0>
+__device__ __forceinline__ void dft_groups_strided(u64 (&v)[32], u32 one) {
+    if constexpr (A > 0 && O < (32 >> A)) {
+        dft_sub_step<INV, A, O, 1, 0, TF21_SHL_WIDE, (32 >> A)>(v, one);
+        dft_groups_strided<INV, A, O + 1>(v, one);
     }
 }
 // 32 / 2^A independent 2^A-point DFTs on the register groups v[g 2^A .. (g + 1) 2^A); out: v[g 2^A + brev_A(k)]
@@ -771,6 +780,106 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt1024_single_k
 }
 
 
+// ---- leading pass of 2^K points, 1 <= K <= 9, in registers (n = 2^11 .. 2^19 and the top digit of n >= 2^21) ----
+// Position preserving like every leading pass: [outer][2^K rows][inner], DFT along the rows, then the twiddle
+// omega_B^(kappa * j_rest).  A warp takes a [2^K rows][G = 2^(10-K) word-columns] tile = 1024 elements, flat index
+// e = row * G + col = 32 a + lane:
+//   K < 5 : the rows are the high K bits of the register index a -- strided register groups, no shared memory;
+//   K >= 5: step A = 32-point DFT over a, twiddle omega_2^K^(kappa1 * b_hi), 32 x 32 transpose, step B =
+//           2^(K-5)-point DFTs over the high bits of b (register groups of stride G); X[kappa1 + 32 kappa2] of
+//           column b_lo sits in lane kappa1; a second pass through the slice restores e-order for coalesced stores.
+// Replaces two thread-per-column passes (<= 32 points each) for 2^16 .. 2^19 and 2^26 .. 2^29.
+struct ColNArgs {
+    const u64 *src;
+    u64 *dst;
+    u64 array_words;    // n * w: distance between arrays (source and destination: plain passes only)
+    u32 inner_words;    // row stride in words (inner_elems * w)
+    u32 w;
+    u32 n_outer;
+    const u64 *tw1;     // K > 5: [32][2^(K-5)] omega_2^K^(+-kappa1 b_hi); else nullptr
+    const u64 *tw_full; // [2^K][inner_elems] scalar * omega_B^(+-kappa j) or nullptr (then the split tables)
+    ScaleTab tw;
+    u32 log_b;
+    u32 scaled;         // the full table carries a scalar other than one (its row 0 is not all ones)
+};
+
+template <bool INV, int K>
+__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt_col_n_kernel(const ColNArgs a) {
+    static_assert(K >= 1 && K <= 9, "leading passes of 2 .. 512 points");
+    constexpr u32 G = 1u << (10 - K);  // word-columns per warp
+    extern __shared__ __align__(16) u64 smem[];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 col0 = (blockIdx.x * kFastCols + warp) * G;
+    if (col0 >= a.inner_words) return;
+    const u32 o = blockIdx.y, b = blockIdx.z;
+    const u64 base = (u64)b * a.array_words + (u64)o * ((u64)a.inner_words << K) + col0;
+    const u64 *src = a.src + base;
+    u64 *dst = a.dst + base;
+    const u32 one = c_gl_one;
+    u64 v[32];
+    // element e = 32 aa + lane: row e >> (10 - K), column e & (G - 1)
+#pragma unroll
+    for (int aa = 0; aa < 32; aa++) {
+        const u32 e = 32 * aa + lane;
+        v[aa] = __ldcs(src + (u64)(e >> (10 - K)) * a.inner_words + (e & (G - 1)));
+    }
+    const u64 bmask = (1ull << a.log_b) - 1;
+    const u32 inner_elems = a.w == 1 ? a.inner_words : a.inner_words / 3u;
+    if constexpr (K <= 5) {
+        dft_groups_strided<INV, K>(v, one);
+        // register brev_K(kappa) * 2^(5-K) + a_lo holds X[kappa] of column a_lo * 32 + lane: coalesced as it is
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const u32 kappa = brev_bits((u32)r >> (5 - K), K), a_lo = (u32)r & ((1u << (5 - K)) - 1);
+            const u32 col = a_lo * 32 + lane;
+            const u32 jrest = a.w == 1 ? col0 + col : (col0 + col) / 3u;
+            u64 x = v[r];
+            if (a.tw_full) {
+                if (kappa != 0 || a.scaled) x = gl_mul(x, __ldg(a.tw_full + (u64)kappa * inner_elems + jrest));
+            } else if (kappa != 0) {
+                x = gl_mul(x, scale_factor_l(a.tw, ((u64)kappa * jrest) & bmask));
+            }
+            __stcs(dst + (u64)kappa * a.inner_words + col, x);
+        }
+    } else {
+        constexpr int BP = K - 5;  // bits of b_hi
+        u64 *slice = smem + warp * kFastS;
+        dft_groups<INV, 5>(v, one);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) {
+            u64 x = v[brev5((u32)k1)];
+            if (k1 != 0) x = gl_mul(x, __ldg(a.tw1 + (k1 << BP) + (lane >> (10 - K))));
+            slice[k1 * kTransposeStride + lane] = x;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int bb = 0; bb < 32; bb++) v[bb] = slice[lane * kTransposeStride + bb];
+        dft_groups_strided<INV, BP>(v, one);
+        __syncwarp();
+        // lane = kappa1; register brev_BP(kappa2) * G + b_lo holds X[kappa1 + 32 kappa2] of column b_lo -> e-order.
+        // One pad word per 16 (slot(e) = e + e / 16): the writes of a half warp (stride G words) and the reads
+        // (consecutive e) both fall on 16 different bank pairs.
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const u32 kappa2 = brev_bits((u32)r >> (10 - K), BP), b_lo = (u32)r & (G - 1);
+            const u32 e = (lane + 32 * kappa2) * G + b_lo;
+            slice[e + (e >> 4)] = v[r];
+        }
+        __syncwarp();
+#pragma unroll 8
+        for (int aa = 0; aa < 32; aa++) {
+            const u32 e = 32 * aa + lane;
+            const u32 kappa = e >> (10 - K), col = e & (G - 1);
+            const u32 jrest = a.w == 1 ? col0 + col : (col0 + col) / 3u;
+            u64 x = slice[e + (e >> 4)];
+            if (a.tw_full) x = gl_mul(x, __ldg(a.tw_full + (u64)kappa * inner_elems + jrest));
+            else x = gl_mul(x, scale_factor_l(a.tw, ((u64)kappa * jrest) & bmask));
+            __stcs(dst + (u64)kappa * a.inner_words + col, x);
+        }
+    }
+}
+
 // ---- n = 2^K < 1024: a warp takes 1024 consecutive elements = 2^(10-K) whole columns, all in registers ------
 // (reference benches at 2^7, benches/ntt.rs:19).  Flat element J of the batch = (array J / n, index J % n); a warp
 // owns J0 .. J0 + 1023 of one coefficient lane (w = 3: the three warps of a chunk interleave like the 2^10 kernel).
@@ -865,6 +974,34 @@ struct FastTables {
 };
 static std::map<int, FastTables> g_fast_tables;  // by device, guarded by g_mutex
 static std::map<std::tuple<int, unsigned, int, u64>, u64 *> g_small_n_tw;  // (device, K, inverse, scalar), guarded by g_mutex
+
+static std::map<std::tuple<int, unsigned, int>, u64 *> g_col_n_tw1;  // (device, K, inverse), guarded by g_mutex
+
+// [32][2^(K-5)] omega_{2^K}^(+-kappa1 b_hi) for the 2^K-point leading pass, 5 < K < 10
+inline int get_col_n_tw1(DeviceTables &t, int dev, unsigned k, int inverse, const u64 **out) {
+    auto key = std::make_tuple(dev, k, inverse);
+    auto it = g_col_n_tw1.find(key);
+    if (it != g_col_n_tw1.end()) {
+        *out = it->second;
+        return 0;
+    }
+    u64 w = hgl_root_of_unity(k);
+    if (inverse) w = hgl_inv(w);
+    const u32 cols = 1u << (k - 5);
+    std::vector<u64> h(32 * cols);
+    for (u32 k1 = 0; k1 < 32; k1++) {
+        u64 step = hgl_pow(w, k1), acc = 1;
+        for (u32 bh = 0; bh < cols; bh++) {
+            h[k1 * cols + bh] = acc;
+            acc = hgl_mul(acc, step);
+        }
+    }
+    u64 *d;
+    TF21_TRY(upload(t, h, &d));
+    g_col_n_tw1[key] = d;
+    *out = d;
+    return 0;
+}
 
 // [2^(K-5)][32] scalar * omega_{2^K}^(+-k1 b) for the 2^K-point kernel, 5 < K < 10
 inline int get_small_n_tw(DeviceTables &t, int dev, unsigned k, int inverse, u64 scalar, const u64 **out) {
@@ -994,6 +1131,14 @@ inline bool post_scalar_is_foldable(u64 post_scalar, u32 n_lead) { return post_s
 inline bool tma_defer_disabled() {
     static const bool off = getenv("TF21_TW_DEFER") == nullptr;
     return off;
+}
+inline bool col_n_disabled() {
+    static const bool off = getenv("TF21_NO_COL_N") != nullptr;
+    return off;
+}
+inline bool col_n_forced() {
+    static const bool on = getenv("TF21_COL_N_ALL") != nullptr;
+    return on;
 }
 inline bool small_n_disabled() {
     static const bool off = getenv("TF21_NO_SMALL_N") != nullptr;
@@ -1244,6 +1389,7 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     u32 lead[3];
     u32 n_lead = 0;
     bool lead_is_col10[3] = {false, false, false};
+    bool first_is_coln = false;
     {
         u32 rem = log_n - 10;
         const bool has_col = rem >= 10;
@@ -1252,8 +1398,14 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         // non-zero rows and replaces two full passes
         const bool prune_all = !inverse && n_in < n && rem >= 1 && rem <= 6 &&
                                nonzero_rows_log(n_in, n >> rem, rem) <= 3 && nonzero_rows_log(n_in, n >> rem, rem) < rem;
-        if (prune_all) {
-            lead[n_lead++] = rem;
+        // The register pass (ntt_col_n_kernel) is taken where it measured faster than the thread-per-column passes
+        // (profiles/r02e_ntt_size_sweep.txt): 2- and 4-point leading passes (2^11, 2^12, 2^21, 2^22: -6 .. -19 %) and
+        // the 64-point pass in front of a 1024-point column pass (2^26: one pass fewer).  In between it is latency
+        // bound (4 warps per scheduler, 41 % issue, profiles/r02e_ncu_col_n_summary.txt) and loses 1 .. 15 %.
+        first_is_coln = !prune_all && n_in == n && !pre.lo && !col_n_disabled() &&
+                        ((rem >= 1 && rem <= 2) || (rem == 6 && has_col) || (col_n_forced() && rem >= 1 && rem <= 9));
+        if (prune_all || first_is_coln) {
+            lead[n_lead++] = rem;  // one pruned pass, or one register pass of 2^rem points (ntt_col_n_kernel)
         } else if (rem > 5) {  // 64-point columns per thread do not pay: ~200 KB of straight-line code, 196 registers
             lead[n_lead++] = (rem + 1) / 2;
             lead[n_lead++] = rem / 2;
@@ -1282,8 +1434,11 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         const u32 log_b = log_n - consumed;
         const u64 inner_words = ((u64)1 << log_inner) * w;
         const u32 n_outer = 1u << consumed;
+        const bool is_coln = p == 0 && first_is_coln;
         u64 scalar = 1;
-        if (p == 0 && post_scalar) {  // fold the unscale (ntt.rs:220-228) into the first twiddle table
+        // fold the unscale (ntt.rs:220-228) into the first twiddle TABLE: a register pass that works from the split
+        // tables (B > 2^20) leaves it to the 1024-point column pass behind it, whose table always exists
+        if (post_scalar && !(is_coln && log_b > kFullTwiddleMaxLog)) {
             scalar = post_scalar;
             post_scalar = 0;
         }
@@ -1304,7 +1459,44 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
                 tw_scalar = scalar == 1 ? 0 : scalar;
             }
         }
-        if (lead_is_col10[p]) {
+        if (is_coln) {
+            ColNArgs a{};
+            a.src = cur_src;
+            a.dst = scratch;
+            a.array_words = array_words;
+            a.inner_words = (u32)inner_words;
+            a.w = w;
+            a.n_outer = n_outer;
+            a.tw_full = tw_full;
+            a.tw = tw;
+            a.log_b = log_b;
+            a.scaled = scalar % GL_P != 1 ? 1u : 0u;
+            if (lp > 5) {
+                std::lock_guard<std::mutex> lock(g_mutex);
+                TF21_TRY(get_col_n_tw1(tabs, dev, lp, inverse, &a.tw1));
+            }
+            const u32 groups = (u32)(inner_words >> (10 - lp));  // word-column groups of G = 2^(10-lp) per block of rows
+            for (u64 b0 = 0; b0 < batch; b0 += 65535) {
+                a.src = cur_src + b0 * array_words;
+                a.dst = scratch + b0 * array_words;
+                const dim3 grid((groups + kFastCols - 1) / kFastCols, n_outer, (unsigned)(batch - b0 < 65535 ? batch - b0 : 65535));
+#define TF21_COL_N_CASE(K_)                                                                                          \
+    case K_:                                                                                                        \
+        if (inverse)                                                                                                \
+            TF21_LAUNCH_NAMED("ntt_col_n_kernel", (ntt_col_n_kernel<true, K_>), grid, kFastThreads,                 \
+                              (K_ <= 5 ? 0 : kFastSmem), st, a);                                                    \
+        else                                                                                                        \
+            TF21_LAUNCH_NAMED("ntt_col_n_kernel", (ntt_col_n_kernel<false, K_>), grid, kFastThreads,                \
+                              (K_ <= 5 ? 0 : kFastSmem), st, a);                                                    \
+        break;
+                switch (lp) {
+                    TF21_COL_N_CASE(1) TF21_COL_N_CASE(2) TF21_COL_N_CASE(3) TF21_COL_N_CASE(4) TF21_COL_N_CASE(5)
+                    TF21_COL_N_CASE(6) TF21_COL_N_CASE(7) TF21_COL_N_CASE(8) TF21_COL_N_CASE(9)
+                    default: return TF21_E_BAD_ARG;
+                }
+#undef TF21_COL_N_CASE
+            }
+        } else if (lead_is_col10[p]) {
             FastColArgs a{};
             a.src = cur_src;
             a.dst = scratch;

@@ -74,7 +74,9 @@ static int get_tables(DeviceTables **out, int *dev_out = nullptr) {
 #undef TF21_FAST_SMEM
 #define TF21_SMALL_N_SMEM(K_)                                                                                          \
     TF21_CUDA(cudaFuncSetAttribute(ntt_small_n_kernel<false, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem)); \
-    TF21_CUDA(cudaFuncSetAttribute(ntt_small_n_kernel<true, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+    TF21_CUDA(cudaFuncSetAttribute(ntt_small_n_kernel<true, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));  \
+    TF21_CUDA(cudaFuncSetAttribute(ntt_col_n_kernel<false, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));   \
+    TF21_CUDA(cudaFuncSetAttribute(ntt_col_n_kernel<true, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         TF21_SMALL_N_SMEM(1) TF21_SMALL_N_SMEM(2) TF21_SMALL_N_SMEM(3) TF21_SMALL_N_SMEM(4) TF21_SMALL_N_SMEM(5)
         TF21_SMALL_N_SMEM(6) TF21_SMALL_N_SMEM(7) TF21_SMALL_N_SMEM(8) TF21_SMALL_N_SMEM(9)
 #undef TF21_SMALL_N_SMEM
@@ -275,6 +277,7 @@ int tf21_shutdown(void) {
     g_devices.clear();
     g_fast_tables.clear();  // their device pointers lived in `owned` and are gone: never hand them out again
     g_small_n_tw.clear();
+    g_col_n_tw1.clear();
     if (prev >= 0) cudaSetDevice(prev);
     return 0;
 }
