@@ -2,6 +2,7 @@
 oracle on identical seeded inputs, against the reference's golden vectors, and -- at full
 BASELINE.json sizes -- through size-independent properties.  Bit-exact everywhere (integer work)."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -945,3 +946,29 @@ def test_small_n_register_kernel(tf, oracle, log2n, width):
         dev.ntt_(d, n, width, True)
         torch.cuda.synchronize()
         assert np.array_equal(d.cpu().numpy().view(np.uint64), x), (log2n, width, batch)
+
+
+def test_register_leading_pass_for_every_size_in_a_subprocess(tf):
+    """ntt_col_n_kernel is only selected where it measured faster; TF21_COL_N_ALL=1 forces it for every leading pass
+    of 2 .. 512 points so that all nine instantiations stay covered (the switch is read once per process)"""
+    import subprocess
+    import sys
+
+    code = r'''
+import importlib, sys, numpy as np
+sys.path.insert(0, %r)
+import oracle
+tf = importlib.import_module("twenty-first_b200")
+o = oracle.get()
+for log2n, w in [(k, 1) for k in range(11, 20)] + [(13, 3), (16, 3), (19, 3), (21, 1), (23, 1), (25, 1)]:
+    x = oracle.splitmix64_words(0xC01 + log2n, (1 << log2n) * w) %% np.uint64(oracle.P)
+    want = x.copy(); assert o.ntt(want, w) == 0
+    got = x.copy(); tf.ntt(got.reshape(-1, w) if w == 3 else got)
+    assert np.array_equal(got, want), (log2n, w)
+    tf.intt(got.reshape(-1, w) if w == 3 else got)
+    assert np.array_equal(got, x), (log2n, w)
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TF21_COL_N_ALL="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

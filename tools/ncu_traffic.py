@@ -1,4 +1,4 @@
-"""Extract per-launch DRAM traffic from .ncu-rep files into profiles/r01_ncu_traffic.json.
+"""Extract per-launch DRAM traffic from .ncu-rep files into profiles/r02_ncu_traffic.json (TF21_TRAFFIC_JSON overrides).
 usage: python tools/ncu_traffic.py shape_key=report.ncu-rep [...]"""
 import csv
 import json
@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-out_path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+out_path = os.environ.get("TF21_TRAFFIC_JSON") or os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
 db = json.load(open(out_path)) if os.path.exists(out_path) else {}
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 for arg in sys.argv[1:]:

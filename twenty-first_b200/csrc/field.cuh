@@ -427,6 +427,27 @@ __device__ __forceinline__ u64 gl_fix(u64 s, u32 c) { return s + (u64)c * GL_EPS
 // into the carry predicate of the IADD3.X and if-converts the two-instruction body, so a lazy add is
 // IADD3, IADD3.X, @P IADD3, @P IADD3.X -- no SEL, no IMAD.WIDE.  Subtraction is a + ~b + 1 so that only
 // add-with-carry instructions appear (borrow and carry flags are never mixed, see gl_canon).
+#ifndef TF21_ADDFIX_WIDE
+#define TF21_ADDFIX_WIDE 0  /* carry correction of the lazy addition as one predicated IMAD.WIDE.U32 (one * EPS + v) */
+#endif
+__device__ __forceinline__ u64 gl_addp_wide(u64 a, u64 t, u32 one) {  // a any, t <= p -> any
+    u64 s;
+    asm("{\n\t.reg .u32 c,lo,hi; .reg .pred p; .reg .u64 v;\n\t"
+        "add.cc.u64 v,%1,%2;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.eq.u32 p,c,0;\n\t"
+        "@p bra GLAW%=;\n\t"
+        "mov.b64 {lo,hi},v;\n\t"
+        "mad.lo.cc.u32 lo,%3,0xffffffff,lo;\n\t"
+        "madc.hi.u32 hi,%3,0xffffffff,hi;\n\t"
+        "mov.b64 v,{lo,hi};\n\t"
+        "GLAW%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(s)
+        : "l"(a), "l"(t), "r"(one));
+    return s;
+}
 __device__ __forceinline__ u64 gl_addp(u64 a, u64 t) {  // a any, t <= p -> any
     u64 s;
     asm("{\n\t.reg .u32 c; .reg .pred p; .reg .u64 v;\n\t"
@@ -507,6 +528,28 @@ __device__ __forceinline__ u64 gl_canonc(u64 x) {
         "}"
         : "=l"(s)
         : "l"(x));
+    return s;
+}
+#ifndef TF21_CANON_WIDE
+#define TF21_CANON_WIDE 0  /* bit 0: canonicalisation of the trivial butterflies, bit 1: of the stored outputs -- x + EPS with its carry-out as ONE IMAD.WIDE.U32 (FMA-heavy pipe) instead of IADD3 + IADD3.X (ALU pipe) */
+#endif
+// x >= p  <=>  x + EPS carries; the sum is one * EPS + x on the FMA-heavy pipe (`one`: see gl_subp)
+__device__ __forceinline__ u64 gl_canon_wide(u64 x, u32 one) {
+    u64 s;
+    asm("{\n\t.reg .u32 lo,hi,wl,wh,c; .reg .pred p; .reg .u64 v;\n\t"
+        "mov.b64 {lo,hi},%1;\n\t"
+        "mad.lo.cc.u32 wl,%2,0xffffffff,lo;\n\t"
+        "madc.hi.cc.u32 wh,%2,0xffffffff,hi;\n\t"
+        "addc.u32 c,0,0;\n\t"
+        "setp.eq.u32 p,c,0;\n\t"
+        "mov.b64 v,%1;\n\t"
+        "@p bra GLCW%=;\n\t"
+        "mov.b64 v,{wl,wh};\n\t"
+        "GLCW%=:\n\t"
+        "mov.b64 %0,v;\n\t"
+        "}"
+        : "=l"(s)
+        : "l"(x), "r"(one));
     return s;
 }
 __device__ __forceinline__ u64 gl_canonp(u64 x) {  // any -> [0, p)

@@ -54,6 +54,9 @@ namespace tf21 {
 #ifndef TF21_SHL_ROW
 #define TF21_SHL_ROW TF21_SHL_WIDE
 #endif
+#ifndef TF21_TW_PREFETCH
+#define TF21_TW_PREFETCH 0  /* measured: 1.356 against 1.341 ms for the column pass (L1 too small next to 4 x 36 KB of shared memory) */
+#endif
 #ifndef TF21_FAST_COLS
 #define TF21_FAST_COLS 4  /* 4 CTAs of 128 threads per SM: finer interleaving of staging and compute phases than 2 x 256 (tools/ab.sh: 3.14 ms against 3.27 ms per 256-column batch once the staging is asynchronous; 32-byte row segments = one DRAM sector) */
 #endif
@@ -107,15 +110,15 @@ __device__ __forceinline__ void dft_pow2_step(u64 (&v)[1 << A], u32 one) {
         constexpr bool neg = E >= 96;
         constexpr int S = neg ? E - 96 : E;
         u64 t;
-        if constexpr (S == 0) t = gl_canonw(v[ib]);
+        if constexpr (S == 0) t = (TF21_CANON_WIDE & 1) ? gl_canon_wide(v[ib], one) : gl_canonw(v[ib]);
         else t = gl_shlc<S, SHLV>(v[ib], one);
         const u64 u = v[iu];
         if constexpr (!neg) {
-            v[iu] = gl_addl(u, t);
+            v[iu] = TF21_ADDFIX_WIDE ? gl_addp_wide(u, t, one) : gl_addl(u, t);
             v[ib] = gl_subl(u, t, one);
         } else {
             v[iu] = gl_subl(u, t, one);
-            v[ib] = gl_addl(u, t);
+            v[ib] = TF21_ADDFIX_WIDE ? gl_addp_wide(u, t, one) : gl_addl(u, t);
         }
         dft_pow2_step<INV, A, LS, IDX + 1, SHLV>(v, one);
     }
@@ -149,15 +152,15 @@ __device__ __forceinline__ void dft_sub_step(u64 (&v)[32], u32 one) {
         constexpr bool neg = E >= 96;
         constexpr int S = neg ? E - 96 : E;
         u64 t;
-        if constexpr (S == 0) t = gl_canonw(v[ib]);
+        if constexpr (S == 0) t = (TF21_CANON_WIDE & 1) ? gl_canon_wide(v[ib], one) : gl_canonw(v[ib]);
         else t = gl_shlc<S, SHLV>(v[ib], one);
         const u64 u = v[iu];
         if constexpr (!neg) {
-            v[iu] = gl_addl(u, t);
+            v[iu] = TF21_ADDFIX_WIDE ? gl_addp_wide(u, t, one) : gl_addl(u, t);
             v[ib] = gl_subl(u, t, one);
         } else {
             v[iu] = gl_subl(u, t, one);
-            v[ib] = gl_addl(u, t);
+            v[ib] = TF21_ADDFIX_WIDE ? gl_addp_wide(u, t, one) : gl_addl(u, t);
         }
         dft_sub_step<INV, A, OFF, LS, IDX + 1, SHLV, STRIDE>(v, one);
     }
@@ -217,7 +220,7 @@ __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64
             }
         } else if (CANON_OUT && it) {  // last pass: canonical words straight into the outgoing tile
 #pragma unroll
-            for (int k = 0; k < 32; k++) out[k * ss] = gl_canonw(v[brev5(k)]);
+            for (int k = 0; k < 32; k++) out[k * ss] = (TF21_CANON_WIDE & 2) ? gl_canon_wide(v[brev5(k)], one) : gl_canonw(v[brev5(k)]);
         } else {
 #pragma unroll
             for (int k = 0; k < 32; k++) out[k * ss] = v[brev5(k)];
@@ -404,6 +407,15 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks)
     const u32 off0 = tma_tile_word(lane, warp);
     const u32 qw = ct * kTmaTileCols + warp;
     const u64 jrest = a.w == 1 ? qw : qw / 3u;
+#if TF21_TW_PREFETCH
+    // the warp's inter-pass twiddle row (8 KiB, an L2 hit ~0.3 us away) is needed right after the second 32-point
+    // step: pull it towards the SM now, two 128-byte lines per lane
+    if (TW) {
+        const char *twp = reinterpret_cast<const char *>(a.tw_full + jrest * 1024) + lane * 128;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(twp));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(twp + 4096));
+    }
+#endif
     mbar_wait(bar, 0);
     u64 v[32];
 #pragma unroll
