@@ -135,12 +135,20 @@ def cpu_reference_leg(steps: int, warmup: int, sample_cols: int | None, merkle_l
     assert np.array_equal(x, orig)
     ntt_per_s = 2 * cols * len(times) / sum(times)
     leafs = oracle.splitmix64_words(0x210002, 5 << merkle_log2)
-    o.merkle_par_new(leafs)
-    t0 = time.perf_counter()
-    reps = max(1, min(steps, 3))
-    for _ in range(reps):
+    # Tip5 in both forms the reference ships: the scalar build (mds_generated, tip5/mod.rs:175-506) and, when this host
+    # has avx512f/bw/ifma/vbmi, its AVX-512 build (tip5/avx512.rs); the faster one is the Merkle baseline
+    merkle_rates = {}
+    for impl in ("scalar", "avx512"):
+        if o.tip5_set_impl(impl) != impl:
+            continue
         o.merkle_par_new(leafs)
-    merkle_s = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        reps = max(1, min(steps, 3))
+        for _ in range(reps):
+            o.merkle_par_new(leafs)
+        merkle_rates[impl] = (1 << merkle_log2) * reps / (time.perf_counter() - t0)
+    o.tip5_set_impl("scalar")
+    merkle_impl = max(merkle_rates, key=merkle_rates.get)
     # BASELINE configs[0]: one 2^10-point BFieldElement ntt -> intt round trip, single thread (the reference's own
     # CPU-runnable case; nearest reference bench shapes are 2^7 / 2^18, benches/ntt.rs:19-21)
     v = oracle.splitmix64_words(0x210000, 1 << 10)
@@ -159,7 +167,8 @@ def cpu_reference_leg(steps: int, warmup: int, sample_cols: int | None, merkle_l
         "config0_roundtrip_us": cfg0_us,
         "ntt_per_s": ntt_per_s, "ms_per_step": 1e3 * sum(times) / len(times), "cores": cores,
         "sample": f"{cols} columns x 2^{LOG2N} forward+inverse per step; Merkle par_new over 2^{merkle_log2} leaves",
-        "merkle_leaves_per_s": (1 << merkle_log2) / merkle_s,
+        "merkle_leaves_per_s": merkle_rates[merkle_impl], "merkle_tip5_impl": merkle_impl,
+        "merkle_leaves_per_s_by_tip5_impl": merkle_rates,
     }
 
 
@@ -202,6 +211,7 @@ def main():
                        "columns_per_gpu": args.cols, "log2_n": LOG2N, "sample": r["sample"]},
             "cpu_baseline": {"value": r["ntt_per_s"], "unit": "NTT/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"], "merkle_leaves_per_s": r["merkle_leaves_per_s"],
+                             "merkle_tip5_impl": r["merkle_tip5_impl"], "merkle_leaves_per_s_by_tip5_impl": r["merkle_leaves_per_s_by_tip5_impl"],
                              "config0_2^10_ntt_intt_roundtrip_us_1thread": r["config0_roundtrip_us"]},
             "e2e": {"value": r["ntt_per_s"], "unit": "NTT/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "merkle": {"value": r["merkle_leaves_per_s"], "unit": "leaves/s"},
@@ -492,7 +502,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_leg(2, 1, args.cpu_cols or args.cols, 22)
         cpu = {"value": r["ntt_per_s"], "unit": "NTT/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
-               "merkle_leaves_per_s": r["merkle_leaves_per_s"],
+               "merkle_leaves_per_s": r["merkle_leaves_per_s"], "merkle_tip5_impl": r["merkle_tip5_impl"],
+               "merkle_leaves_per_s_by_tip5_impl": r["merkle_leaves_per_s_by_tip5_impl"],
                "config0_2^10_ntt_intt_roundtrip_us_1thread": r["config0_roundtrip_us"]}
 
     if rank == 0:

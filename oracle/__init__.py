@@ -31,11 +31,15 @@ E_ORDER_LE_DEGREE = -5
 E_LEAF_INDEX_INVALID = -9
 
 
+_AVX512_FLAGS = ["-mavx512f", "-mavx512bw", "-mavx512ifma", "-mavx512vbmi"]
+
+
 def build(native: bool = False, force: bool = False) -> str:
-    """Compile oracle.c with gcc. native=True uses -march=native (for CPU-baseline timing on
-    the box the benchmark runs on) and writes a separate file."""
+    """Compile oracle.c (+ tip5_avx512.c with the four -mavx512* flags, used only when the HOST has them) with gcc.
+    native=True uses -march=native for oracle.c (CPU-baseline timing on the box the benchmark runs on) and writes a
+    separate file."""
     out = os.path.join(_BUILD, "liboracle_native.so" if native else "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "field.h", "tip5_mds_generated.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "field.h", "tip5_mds_generated.h", "tip5_avx512.c")]
     if not force and os.path.exists(out) and all(
         os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs
     ):
@@ -43,8 +47,14 @@ def build(native: bool = False, force: bool = False) -> str:
     os.makedirs(_BUILD, exist_ok=True)
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     march = "native" if native else "x86-64-v3"
-    cmd = [cc, "-O3", f"-march={march}", "-fopenmp", "-fPIC", "-std=gnu11", "-shared",
-           "-o", out, os.path.join(_HERE, "oracle.c")]
+    tag = "native" if native else "base"
+    avx_obj = os.path.join(_BUILD, f"tip5_avx512_{tag}.o")
+    avx = subprocess.run([cc, "-O3", "-march=x86-64-v3", *_AVX512_FLAGS, "-fPIC", "-std=gnu11", "-c",
+                          "-o", avx_obj, os.path.join(_HERE, "tip5_avx512.c")], cwd=_HERE, capture_output=True)
+    cmd = [cc, "-O3", f"-march={march}", "-fopenmp", "-fPIC", "-std=gnu11", "-shared", "-o", out,
+           os.path.join(_HERE, "oracle.c")]
+    if avx.returncode == 0:  # a compiler without the intrinsics just leaves the AVX-512 leg out
+        cmd += ["-DTF21_ORACLE_AVX512", avx_obj]
     subprocess.run(cmd, check=True, cwd=_HERE)
     return out
 
@@ -84,6 +94,11 @@ class Oracle:
         L.oracle_tip5_permutation.restype = None
         L.oracle_tip5_hash_rows_batch.argtypes = [_u64p, u64, u64, _u64p, i32]
         L.oracle_tip5_hash_rows_batch.restype = None
+        L.oracle_tip5_avx512_available.restype = i32
+        L.oracle_tip5_set_impl.argtypes = [i32]
+        L.oracle_tip5_set_impl.restype = i32
+        L.oracle_tip5_round_avx512.argtypes = [_u64p, i32]
+        L.oracle_tip5_round_avx512.restype = i32
         L.oracle_tip5_round.argtypes = [_u64p, i32]
         L.oracle_tip5_round.restype = None
         L.oracle_tip5_round_naive.argtypes = [_u64p, i32]
@@ -225,6 +240,18 @@ class Oracle:
         """one round in place: the scalar build's form (mds_generated) or NaiveTip5's (tip5/naive.rs:26-76)"""
         assert state.size == 16
         (self.lib.oracle_tip5_round_naive if naive else self.lib.oracle_tip5_round)(_ptr(state), round_index)
+
+    def tip5_avx512_available(self) -> bool:
+        """the AVX-512 IFMA/VBMI round (tip5/avx512.rs) was built and this host can run it"""
+        return bool(self.lib.oracle_tip5_avx512_available())
+
+    def tip5_set_impl(self, impl: str) -> str:
+        """'scalar' (mds_generated, tip5/mod.rs:175-506) or 'avx512' (tip5/avx512.rs); returns what is in effect"""
+        return "avx512" if self.lib.oracle_tip5_set_impl(1 if impl == "avx512" else 0) == 1 else "scalar"
+
+    def tip5_round_avx512(self, state: np.ndarray, round_index: int) -> bool:
+        assert state.size == 16
+        return self.lib.oracle_tip5_round_avx512(_ptr(state), round_index) == 0
 
     def tip5_permute_batch(self, states: np.ndarray, threads: int = 0) -> None:
         self.lib.oracle_tip5_permute_batch(_ptr(states), states.size // 16, threads)

@@ -290,6 +290,14 @@ static const uint64_t MDS_FIRST_COLUMN[STATE_SIZE] = {
     56951, 27521, 41351, 40901, 12021, 59689, 26798, 17845,
 };
 
+/* AVX-512 IFMA/VBMI round (tip5_avx512.c <- tip5/avx512.rs), present when the build had the flags */
+#ifdef TF21_ORACLE_AVX512
+void oracle_tip5_avx512_setup(const uint64_t mds_first_column[16], const uint64_t rc_raw[80], const uint8_t lut[256]);
+void oracle_tip5_avx512_permutation(uint64_t state[16]);
+void oracle_tip5_avx512_round(uint64_t state[16], int round);
+#endif
+static int g_tip5_impl = 0; /* 0 = scalar (mds_generated), 1 = AVX-512 */
+
 static void tip5_setup(void) {
     if (g_tip5_ready) return;
 #pragma omp critical(tf21_oracle_tip5)
@@ -304,6 +312,9 @@ static void tip5_setup(void) {
             }
             for (int i = 0; i < NUM_ROUNDS * STATE_SIZE; i++) g_rc_raw[i] = bfe_new(ROUND_CONSTANTS[i]);
             for (int i = 0; i < STATE_SIZE; i++) g_mds_raw[i] = bfe_new(MDS_FIRST_COLUMN[i]);
+#ifdef TF21_ORACLE_AVX512
+            oracle_tip5_avx512_setup(MDS_FIRST_COLUMN, g_rc_raw, g_lut);
+#endif
             g_tip5_ready = 1;
         }
     }
@@ -384,9 +395,46 @@ void oracle_tip5_round(uint64_t s[16], int round) {
     tip5_round(s, round);
 }
 
+/* 1 if this build holds the AVX-512 round AND the host has avx512f/bw/ifma/vbmi (the reference's cfg, tip5/mod.rs:36-46) */
+int oracle_tip5_avx512_available(void) {
+#ifdef TF21_ORACLE_AVX512
+    return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+           __builtin_cpu_supports("avx512ifma") && __builtin_cpu_supports("avx512vbmi");
+#else
+    return 0;
+#endif
+}
+
+/* selects the round every hash below uses: 0 = scalar build (mds_generated), 1 = AVX-512 build; returns the choice made */
+int oracle_tip5_set_impl(int impl) {
+    tip5_setup();
+    g_tip5_impl = (impl == 1 && oracle_tip5_avx512_available()) ? 1 : 0;
+    return g_tip5_impl;
+}
+
+/* Tip5::round of the AVX-512 build (tip5/avx512.rs:13-18); -1 when not available */
+int oracle_tip5_round_avx512(uint64_t s[16], int round) {
+#ifdef TF21_ORACLE_AVX512
+    if (!oracle_tip5_avx512_available()) return -1;
+    tip5_setup();
+    oracle_tip5_avx512_round(s, round);
+    return 0;
+#else
+    (void)s;
+    (void)round;
+    return -1;
+#endif
+}
+
 /* Tip5::permutation, tip5/mod.rs:529-533 */
 void oracle_tip5_permutation(uint64_t state[16]) {
     tip5_setup();
+#ifdef TF21_ORACLE_AVX512
+    if (g_tip5_impl == 1) {
+        oracle_tip5_avx512_permutation(state);
+        return;
+    }
+#endif
     for (int r = 0; r < NUM_ROUNDS; r++) tip5_round(state, r);
 }
 

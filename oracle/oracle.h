@@ -50,6 +50,9 @@ void oracle_tip5_permutation(uint64_t state[16]);
 /* one round in the scalar build's form (mds_generated, tip5/mod.rs:175-253) and in NaiveTip5's (tip5/naive.rs:26-76) */
 void oracle_tip5_hash_rows_batch(const uint64_t *rows, uint64_t row_len, uint64_t n_rows, uint64_t *out, int threads);
 void oracle_tip5_round(uint64_t state[16], int round);
+int oracle_tip5_avx512_available(void);
+int oracle_tip5_set_impl(int impl);
+int oracle_tip5_round_avx512(uint64_t state[16], int round);
 void oracle_tip5_round_naive(uint64_t state[16], int round);
 void oracle_tip5_hash_10(const uint64_t in[10], uint64_t out[5]);
 void oracle_tip5_hash_pair(const uint64_t left[5], const uint64_t right[5], uint64_t out[5]);

@@ -1,6 +1,7 @@
 """Pins the CPU oracle against every known-answer test the reference holds for the hot path
 (SURVEY.md 8c).  CPU only."""
 import numpy as np
+import pytest
 
 P = 0xFFFFFFFF00000001
 
@@ -404,3 +405,33 @@ def test_tip5_mds_generated_equals_naive_round(oracle):
             oracle.tip5_round(b, r, naive=True)
             assert np.array_equal(a, b), (k, r)
             assert (a < np.uint64(P)).all()  # the round-constant addition leaves canonical words (:1122-1142)
+
+
+def test_tip5_avx512_round_equals_scalar_round_and_kats(oracle, kats):
+    """the reference keeps its Tip5 snapshots to pin the AVX-512 build against the scalar one (tip5/mod.rs:1285-1295):
+    the restated AVX-512 round (oracle/tip5_avx512.c <- tip5/avx512.rs) must agree round by round and on the KATs"""
+    if not oracle.tip5_avx512_available():
+        pytest.skip("host without avx512f/bw/ifma/vbmi (or gcc without the intrinsics)")
+    from oracle import P, splitmix64_words
+
+    states = [splitmix64_words(0xA512 + i, 16) % np.uint64(P) for i in range(300)]
+    states += [np.full(16, P - 1, dtype=np.uint64), np.zeros(16, dtype=np.uint64), np.arange(16, dtype=np.uint64),
+               np.full(16, 0xFFFFFFFF00000000, dtype=np.uint64)]
+    for k, st in enumerate(states):
+        for r in range(5):
+            a, b = st.copy(), st.copy()
+            oracle.tip5_round(a, r)
+            assert oracle.tip5_round_avx512(b, r)
+            assert np.array_equal(a, b), (k, r)
+    try:
+        assert oracle.tip5_set_impl("avx512") == "avx512"
+        test_tip5_hash10_snapshot(oracle, kats)
+        test_tip5_hash_varlen_snapshot(oracle, kats)
+        test_tip5_raw_state_snapshot(oracle, kats)
+        leafs = splitmix64_words(0xA513, 5 << 10) % np.uint64(P)
+        rc, nodes_avx = oracle.merkle_par_new(leafs)
+        oracle.tip5_set_impl("scalar")
+        rc2, nodes_scalar = oracle.merkle_par_new(leafs)
+        assert rc == 0 and rc2 == 0 and np.array_equal(nodes_avx, nodes_scalar)
+    finally:
+        oracle.tip5_set_impl("scalar")
