@@ -71,7 +71,10 @@ constexpr u32 kTransposeStride = 33;
 constexpr u32 kFastS = kFastCols == 4 ? 1060 : kFastCols == 8 ? 1058 : 1057;
 #endif
 constexpr u32 kFastThreads = kFastCols * 32;
-constexpr u32 kFastMinBlocks = 16 / kFastCols;  // 512 threads of 128 registers per SM (the 32 x u64 column of a lane needs 64)
+#ifndef TF21_MIN_BLOCKS
+#define TF21_MIN_BLOCKS (16 / TF21_FAST_COLS)
+#endif
+constexpr u32 kFastMinBlocks = TF21_MIN_BLOCKS;  // 512 threads of 128 registers per SM (the 32 x u64 column of a lane needs 64)
 constexpr u32 kStageRowsPerIt = 32 / kFastCols;  // rows covered by one warp instruction of the staging loops
 constexpr u32 kStageRowsPerWarp = 1024 / kFastCols;
 constexpr size_t kFastSmem = (size_t)kFastCols * kFastS * sizeof(u64);
@@ -372,6 +375,10 @@ struct ColTmaArgs {
 };
 
 constexpr u32 kTmaTileWords = 1024 * kTmaTileCols;                       // 32 KiB
+#ifndef TF21_TMA_MIN_BLOCKS
+#define TF21_TMA_MIN_BLOCKS 5  /* 5 CTAs of 128 threads per SM (96 registers, no spills): 2.418 -> 2.390 ms per batch; 6 (80 registers) spills: 2.66 ms */
+#endif
+constexpr u32 kTmaMinBlocks = TF21_TMA_MIN_BLOCKS;
 constexpr size_t kColTmaSmem = kFastSmem + 1024 /* alignment slack */ + 16 /* mbarrier */;
 
 // Same arithmetic as ntt1024_col_kernel<INV, true>; the tile travels by TMA.  Shared memory: one region that is
@@ -380,7 +387,7 @@ constexpr size_t kColTmaSmem = kFastSmem + 1024 /* alignment slack */ + 16 /* mb
 // TW = false: the inter-pass twiddles are left to the load of the row pass (ntt1024_row_tma_kernel<.., true>: the
 // table omega_2^20^(i j) is symmetric, so the row pass reads it coalesced next to its data and both latencies overlap).
 template <bool INV, bool TW>
-__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks)
+__global__ void __launch_bounds__(kFastThreads, kTmaMinBlocks)
     ntt1024_col_tma_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map,
                            const ColTmaArgs a) {
     static_assert(kFastCols == kTmaTileCols, "one warp per word-column of the tile");
@@ -574,7 +581,7 @@ struct RowTmaArgs {
 // the second 32-point step writes canonical words into the [1024 rows][4 word-columns] tile in TMA layout and one
 // thread sends it to dst viewed as [batch][1024][rows * W] with four box stores.
 template <bool INV, u32 W, bool TWIN>
-__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks)
+__global__ void __launch_bounds__(kFastThreads, kTmaMinBlocks)
     ntt1024_row_tma_kernel(const __grid_constant__ CUtensorMap dst_map, const RowTmaArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *tile = reinterpret_cast<u64 *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
