@@ -619,7 +619,10 @@ __device__ __forceinline__ u64 gl_canonw(u64 x) {
 // x * 2^S mod p with a CANONICAL result; x any u64; compile-time 0 < S < 96 with S % 32 != 0
 // (every shift twiddle of a 32- or 64-point transform: S is a multiple of 3).
 // z = x << (S % 32) as three 32-bit limbs, then fold by 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32.
-template <int S, int V = TF21_SHL_WIDE>
+// LAZY0: for S < 32 the result is only folded (any u64, < 2^64 - 2^32 unless its high word is 0xffffffff): the
+// optimistic 32-point transform of ntt_fast.cuh checks the high words of a whole stage at once instead of
+// canonicalising every operand.
+template <int S, int V = TF21_SHL_WIDE, bool LAZY0 = false>
 __device__ __forceinline__ u64 gl_shlc(u64 x, u32 one = c_gl_one) {
     static_assert(S > 0 && S < 96 && (S & 31) != 0, "shift twiddle out of range");
     constexpr int q = S >> 5, t = S & 31;
@@ -652,7 +655,9 @@ __device__ __forceinline__ u64 gl_shlc(u64 x, u32 one = c_gl_one) {
         z1 = __funnelshift_l(x0, x1, t);
         z2 = x1 >> (32 - t);  // < 2^31
     }
-    if constexpr (q == 0) {
+    if constexpr (q == 0 && LAZY0) {
+        return gl_reduce96(gl_pack(z0, z1), z2);
+    } else if constexpr (q == 0) {
         // (z1:z0) + z2 * EPS, z2 * EPS < 2^63: at most one wrap; carry and "r >= p" are exclusive
         u32 lo, hi, c;
         asm("mad.lo.cc.u32 %0,%5,0xffffffff,%3;\n\tmadc.hi.cc.u32 %1,%5,0xffffffff,%4;\n\taddc.u32 %2,0,0;"

@@ -54,8 +54,17 @@ namespace tf21 {
 #ifndef TF21_SHL_ROW
 #define TF21_SHL_ROW TF21_SHL_WIDE
 #endif
+#ifndef TF21_FIXW_COL
+#define TF21_FIXW_COL 0
+#endif
+#ifndef TF21_FIXW_ROW
+#define TF21_FIXW_ROW 0
+#endif
 #ifndef TF21_TW_PREFETCH
 #define TF21_TW_PREFETCH 0  /* measured: 1.356 against 1.341 ms for the column pass (L1 too small next to 4 x 36 KB of shared memory) */
+#endif
+#ifndef TF21_DFT_EXIT_MID
+#define TF21_DFT_EXIT_MID 0
 #endif
 #ifndef TF21_FAST_COLS
 #define TF21_FAST_COLS 4  /* 4 CTAs of 128 threads per SM: finer interleaving of staging and compute phases than 2 x 256 (tools/ab.sh: 3.14 ms against 3.27 ms per 256-column batch once the staging is asynchronous; 32-byte row segments = one DRAM sector) */
@@ -132,9 +141,91 @@ __device__ __forceinline__ void dft_pow2(u64 (&v)[1 << A], u32 one = c_gl_one) {
     dft_pow2_step<INV, A, 1, 0, SHLV>(v, one);
 }
 
+// ---- optimistic canonicalisation -------------------------------------------------------------------------------
+// The lazy butterflies need their twiddled operand t <= p.  A lazy value (a sum, a difference, a folded product or
+// shift) is >= p only when its high word is 0xffffffff -- one value in 2^32 for random data -- yet dft_pow2_step pays
+// a canonicalisation (2 ALU + 2 FMA-pipe instructions) for each of the 31 operands with a trivial twiddle and inside
+// each of the 13 shifts by less than 32 bits of a 32-point transform.  Here a stage first forms all its twiddled
+// operands in place (shifts by < 32 bits only folded), takes the maximum of the high words that are not known to be
+// canonical (one three-input VIMNMX per two operands), and only a warp in which some lane saw 0xffffffff
+// canonicalises them (a warp-uniform branch around the old code); then the 16 add / subtract pairs follow.
+// 176 -> ~40 instructions per 32-point transform; bit-exact for every input (the slow path is the old path; adversarial
+// words in tests/test_gpu_parity.py take it).
+#ifndef TF21_OPT_CANON
+#define TF21_OPT_CANON 1
+#endif
+template <bool INV, int A, int LS, int IDX>
+struct DftBfly {
+    static constexpr int N = 1 << A;
+    static constexpr int EU = (39 << (6 - A)) % 192;
+    static constexpr int m = 1 << LS, half = m >> 1;
+    static constexpr int k = (IDX / half) * m, j = IDX % half;
+    static constexpr int iu = brev_bits(k + j, A), ib = brev_bits(k + j + half, A);
+    static constexpr int E0 = (EU * j * (N / m)) % 192;
+    static constexpr int E = INV ? (192 - E0) % 192 : E0;
+    static constexpr bool neg = E >= 96;
+    static constexpr int S = neg ? E - 96 : E;
+    static constexpr bool flagged = S < 32;  // trivial twiddle or a shift that is only folded
+};
+template <bool INV, int A, int LS, int IDX, int SHLV>
+__device__ __forceinline__ void dft_opt_twiddle(u64 (&v)[1 << A], u32 one, u32 &mx) {
+    if constexpr (IDX < (1 << A) / 2) {
+        using B = DftBfly<INV, A, LS, IDX>;
+        if constexpr (B::S != 0) v[B::ib] = gl_shlc<(B::S ? B::S : 1), (SHLV & 15), true>(v[B::ib], one);
+        if constexpr (B::flagged) mx = max(mx, (u32)(v[B::ib] >> 32));
+        dft_opt_twiddle<INV, A, LS, IDX + 1, SHLV>(v, one, mx);
+    }
+}
+template <bool INV, int A, int LS, int IDX>
+__device__ __forceinline__ void dft_opt_fix(u64 (&v)[1 << A]) {
+    if constexpr (IDX < (1 << A) / 2) {
+        using B = DftBfly<INV, A, LS, IDX>;
+        if constexpr (B::flagged) v[B::ib] = gl_canonw(v[B::ib]);
+        dft_opt_fix<INV, A, LS, IDX + 1>(v);
+    }
+}
+// FIXW = K > 0: every K-th sum takes its wrap correction as one predicated IMAD.WIDE.U32 (one * EPS + s, FMA-heavy
+// pipe, 5.3 cycles) instead of IADD3 + IMAD.X (2 cycles of the ALU pipe + 2 of the FMA-heavy pipe)
+template <bool INV, int A, int LS, int IDX, int FIXW>
+__device__ __forceinline__ void dft_opt_addsub(u64 (&v)[1 << A], u32 one) {
+    if constexpr (IDX < (1 << A) / 2) {
+        using B = DftBfly<INV, A, LS, IDX>;
+        const u64 u = v[B::iu], t = v[B::ib];
+        constexpr bool wide = FIXW > 0 && (IDX % (FIXW > 0 ? FIXW : 1)) == 0;
+        if constexpr (!B::neg) {
+            v[B::iu] = wide ? gl_addp_wide(u, t, one) : gl_addl(u, t);
+            v[B::ib] = gl_subl(u, t, one);
+        } else {
+            v[B::iu] = gl_subl(u, t, one);
+            v[B::ib] = wide ? gl_addp_wide(u, t, one) : gl_addl(u, t);
+        }
+        dft_opt_addsub<INV, A, LS, IDX + 1, FIXW>(v, one);
+    }
+}
+// must be called by all 32 lanes of a warp together
+template <bool INV, int A, int LS, int SHLV>
+__device__ __forceinline__ void dft_opt_stage(u64 (&v)[1 << A], u32 one) {
+    if constexpr (LS <= A) {
+        u32 mx = 0;
+        dft_opt_twiddle<INV, A, LS, 0, SHLV>(v, one, mx);
+        if (__any_sync(0xffffffffu, mx == 0xffffffffu)) dft_opt_fix<INV, A, LS, 0>(v);
+        dft_opt_addsub<INV, A, LS, 0, (SHLV >> 4)>(v, one);
+        dft_opt_stage<INV, A, LS + 1, SHLV>(v, one);
+    }
+}
+
 template <bool INV, int SHLV = TF21_SHL_WIDE>
 __device__ __forceinline__ void dft32(u64 (&v)[32], u32 one = c_gl_one) {
     dft_pow2<INV, 5, SHLV>(v, one);
+}
+// the 32-point transform of the warp-per-column passes (whole warps only)
+template <bool INV, int SHLV = TF21_SHL_WIDE>
+__device__ __forceinline__ void dft32_warp(u64 (&v)[32], u32 one = c_gl_one) {
+#if TF21_OPT_CANON
+    dft_opt_stage<INV, 5, 1, SHLV>(v, one);  // SHLV: shift form + 16 * FIXW
+#else
+    dft_pow2<INV, 5, (SHLV & 15)>(v, one);
+#endif
 }
 
 // the same butterflies on the 2^A consecutive registers v[OFF .. OFF + 2^A) of a 32-register column
@@ -204,9 +295,57 @@ __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64
                                              u64 *out1 = nullptr, u32 ss1 = 32u) {
     // 1 in a register of its own: t1[0] = omega_1024^0 (see gl_subp); a global load is never re-issued by ptxas
     const u32 one = (u32)__ldg(tw0 - lane);
+#if TF21_DFT_EXIT_MID
+    // Same two steps with the loop left in the middle: the output phase of the second step sits behind the loop,
+    // where the compiler knows that v[] is dead (in the rolled form below every canonicalised / multiplied word is
+    // first copied, because v[] looks live across the back edge: 8 instead of 4 instructions per stored word)
+#pragma unroll 1
+    for (int it = 0;; it++) {
+        dft32_warp<INV, SHLV>(v, one);
+        if (it) break;
+        u64 *out = slice + lane;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            if (k == 0) {  // t1[0][b] = omega_1024^0 = 1
+                out[0] = v[0];
+                continue;
+            }
+            out[k * kTransposeStride] =
+                MASKMUL ? gl_mul_mask(v[brev5(k)], __ldg(tw0 + 32 * k)) : gl_mul(v[brev5(k)], __ldg(tw0 + 32 * k));
+        }
+        __syncwarp();
+        const ulonglong2 *rowp = reinterpret_cast<const ulonglong2 *>(slice + lane * kTransposeStride);
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const ulonglong2 p = rowp[b];
+            v[2 * b] = p.x;
+            v[2 * b + 1] = p.y;
+        }
+    }
+    {
+        u64 *out = TILE_OUT ? out1 : slice + lane;
+        const u32 ss = TILE_OUT ? ss1 : 32u;
+        if (TILE_OUT) __syncthreads();  // every warp has read its transposed column back
+        __syncwarp();
+        if (tw1) {
+#pragma unroll
+            for (int k = 0; k < 32; k++)
+                out[k * ss] = MASKMUL ? gl_mul_mask(v[brev5(k)], __ldg(tw1 + 32 * k)) : gl_mul(v[brev5(k)], __ldg(tw1 + 32 * k));
+        } else if (CANON_OUT) {  // last pass: canonical words straight into the outgoing tile
+#pragma unroll
+            for (int k = 0; k < 32; k++) out[k * ss] = gl_canonw(v[brev5(k)]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; k++) out[k * ss] = v[brev5(k)];
+        }
+        __syncwarp();
+    }
+    return;
+#endif
 #pragma unroll 1
     for (int it = 0; it < 2; it++) {
-        dft32<INV, SHLV>(v, one);
+        dft32_warp<INV, SHLV>(v, one);
         const u64 *tw = it ? tw1 : tw0;
         u64 *out = (TILE_OUT && it) ? out1 : slice + lane;
         const u32 ss = it ? (TILE_OUT ? ss1 : 32u) : kTransposeStride;
@@ -222,8 +361,21 @@ __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64
                 out[k * ss] = MASKMUL ? gl_mul_mask(v[brev5(k)], __ldg(tw + 32 * k)) : gl_mul(v[brev5(k)], __ldg(tw + 32 * k));
             }
         } else if (CANON_OUT && it) {  // last pass: canonical words straight into the outgoing tile
+#if TF21_OPT_CANON
+            // optimistic: one maximum over the 32 high words; the canonicalisation only runs in a warp that saw 0xffffffff
+            u32 mx = 0;
+#pragma unroll
+            for (int k = 0; k < 32; k++) mx = max(mx, (u32)(v[k] >> 32));
+            if (__any_sync(0xffffffffu, mx == 0xffffffffu)) {
+#pragma unroll
+                for (int k = 0; k < 32; k++) v[k] = gl_canonw(v[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 32; k++) out[k * ss] = v[brev5(k)];
+#else
 #pragma unroll
             for (int k = 0; k < 32; k++) out[k * ss] = (TF21_CANON_WIDE & 2) ? gl_canon_wide(v[brev5(k)], one) : gl_canonw(v[brev5(k)]);
+#endif
         } else {
 #pragma unroll
             for (int k = 0; k < 32; k++) out[k * ss] = v[brev5(k)];
@@ -397,6 +549,8 @@ __global__ void __launch_bounds__(kFastThreads, kTmaMinBlocks)
     u64 *tile = reinterpret_cast<u64 *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     u64 *bar = tile + kFastCols * kFastS;  // 8-byte aligned, behind the private slices
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (tiles fastest: CTAs resident together read adjacent 32-byte segments of the same rows.  Slabs fastest -- so that
+    // resident CTAs share their inter-pass twiddle rows in L1 -- measured 1.57 ms against 1.31 ms: DRAM locality wins)
     const u32 ct = blockIdx.x, slab = a.slab0 + blockIdx.y;
     if (tid == 0) {
         tma_prefetch_map(&src_map);
@@ -428,7 +582,7 @@ __global__ void __launch_bounds__(kFastThreads, kTmaMinBlocks)
 #pragma unroll
     for (int aa = 0; aa < 32; aa++) v[aa] = tile[off0 + 128 * aa];
     __syncthreads();  // the landing zone is dead: it becomes the private slices
-    dft1024_warp<INV, TF21_COL_MASKMUL, TF21_SHL_COL, true>(v, tile + warp * kFastS, a.t1 + lane,
+    dft1024_warp<INV, TF21_COL_MASKMUL, TF21_SHL_COL + 16 * TF21_FIXW_COL, true>(v, tile + warp * kFastS, a.t1 + lane,
                                                             TW ? a.tw_full + jrest * 1024 + lane : nullptr, lane,
                                                             tile + off0, 128u);
     fence_proxy_async_smem();  // my generic-proxy writes of the outgoing tile -> visible to the TMA engine
@@ -606,7 +760,7 @@ __global__ void __launch_bounds__(kFastThreads, kTmaMinBlocks)
         for (int aa = 0; aa < 32; aa++) v[aa] = row[(32 * aa + lane) * W];
     }
     const u32 off0 = tma_tile_word(lane, warp);
-    dft1024_warp<INV, false, TF21_SHL_ROW, true, true>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane, tile + off0, 128u);
+    dft1024_warp<INV, false, TF21_SHL_ROW + 16 * TF21_FIXW_ROW, true, true>(v, tile + warp * kFastS, a.t1 + lane, nullptr, lane, tile + off0, 128u);
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {

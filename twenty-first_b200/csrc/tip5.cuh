@@ -91,6 +91,99 @@ __device__ __forceinline__ u32 tip5_lut_word(u32 w, const uint8_t *s_lut) {
 // One round.  NVAR = 16 in general; NVAR = 10 for the first round of fixed-length hashing
 // (hash_10 / hash_pair, tip5/mod.rs:511-526, 559-586) where lanes 10..15 hold the constant ONE: their
 // S-box outputs and MDS contributions are folded into the round-0 constants rc_lo / rc_hi passed in.
+#ifndef TIP5_FUSED
+#define TIP5_FUSED 0  /* MDS of round r and S-box of round r + 1 interleaved output pair by output pair (tip5_mds_sbox) */
+#endif
+#ifndef TIP5_FUSED_FENCE
+#define TIP5_FUSED_FENCE 1
+#endif
+// 0.0 that ptxas cannot see through (a __device__ variable may be rewritten by the host): see tip5_mds_sbox
+__device__ double g_tip5_zero = 0.0;
+
+__device__ __forceinline__ u64 tip5_sbox_lut(u64 x, const uint8_t *s_lut) {
+    return gl_pack(tip5_lut_word((u32)x, s_lut), tip5_lut_word((u32)(x >> 32), s_lut));
+}
+__device__ __forceinline__ u64 tip5_sbox_pow7(u64 x) {
+#if TIP5_SQR
+    const u64 x2 = gl_sqr(x);
+    const u64 x4 = gl_sqr(x2);
+#else
+    const u64 x2 = TIP5_MUL(x, x);
+    const u64 x4 = TIP5_MUL(x2, x2);
+#endif
+    return TIP5_MUL(x, TIP5_MUL(x2, x4));
+}
+
+// MDS of one round followed (SBOX) by the S-box of the NEXT round, output pair by output pair.
+// In tip5_round below a warp runs an integer phase (S-box: ~1100 instructions bound by the quarter-rate wide
+// multiplies of the FMA-heavy pipe) and then an FP64 phase (MDS); ncu showed the two pipes busy 63 % + 27 % of the
+// time: the phases did not overlap, not even across the four warps of a scheduler.  Here the x^7 of lanes (i, i + 8)
+// depends only on the 32 multiply-adds of output pair i, so the multiply-adds of the later pairs are independent
+// work that fills the issue slots between the dependent integer instructions: every stretch of the instruction
+// stream carries work for the FMA-heavy, the ALU and the FP64 pipe.  (Feeding the accumulators from the S-box side
+// instead -- lane pair j into all 32 accumulators -- was tried first: ptxas sinks the multiply-adds, which then have
+// no consumer until the end of the round, into one block behind the integer work.)
+// in: s = S-box output of this round (NVAR variable lanes); out: s = S-box input of the next round, S-box applied
+// when SBOX (lanes 0..3 canonical before their table look-up).
+template <int NVAR, bool SBOX>
+__device__ __forceinline__ void tip5_mds_sbox(u64 (&s)[TIP5_STATE], const uint8_t *s_lut, const double *rc_lo,
+                                              const double *rc_hi, const double zero) {
+    double al[8], ah[8], bl[8], bh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const double xl = __uint2double_rn((u32)s[j]), xh = __uint2double_rn((u32)(s[j] >> 32));
+        if (j + 8 < NVAR) {
+            const double yl = __uint2double_rn((u32)s[j + 8]), yh = __uint2double_rn((u32)(s[j + 8] >> 32));
+            al[j] = xl + yl;
+            bl[j] = xl - yl;
+            ah[j] = xh + yh;
+            bh[j] = xh - yh;
+        } else {  // lane j + 8 is constant: folded into the seeds
+            al[j] = bl[j] = xl;
+            ah[j] = bh[j] = xh;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        // seeds: round-constant halves.  `zero * dep` (an opaque 0.0 times a finite double made of the S-box output
+        // of pair i - 2) is a scheduling fence: without it ptxas issues all 256 multiply-adds of the round first (they
+        // only depend on a / b) and the integer work afterwards -- the two phases this function exists to interleave.
+        // With it the multiply-adds of pair i become ready when the S-box of pair i - 2 is done, i.e. they run next to
+        // the S-box of pair i - 1 and are finished when that one ends.
+        double pl = rc_lo[i], ph = rc_hi[i], ql = rc_lo[8 + i], qh = rc_hi[8 + i];
+#if TIP5_FUSED_FENCE
+        if (SBOX && i >= 2) {
+            const double dep = __hiloint2double(0x43300000, (int)(u32)s[i - 2 + 8]);
+            pl = fma(zero, dep, pl);
+            ph = fma(zero, dep, ph);
+            ql = fma(zero, dep, ql);
+            qh = fma(zero, dep, qh);
+        }
+#endif
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = (i - j) & 7;
+            const double mp = 0.5 * ((double)TIP5_MDS(k) + (double)TIP5_MDS(k + 8));
+            const double mn = (j <= i ? 0.5 : -0.5) * ((double)TIP5_MDS(k) - (double)TIP5_MDS(k + 8));
+            pl = fma(mp, al[j], pl);
+            ph = fma(mp, ah[j], ph);
+            ql = fma(mn, bl[j], ql);
+            qh = fma(mn, bh[j], qh);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const u64 acc_lo = __double2ull_rn(half ? pl - ql : pl + ql);
+            const u64 acc_hi = __double2ull_rn(half ? ph - qh : ph + qh);
+            const u64 x0 = acc_lo + (acc_hi << 32);
+            const u32 x1 = (u32)(acc_hi >> 32) + (x0 < acc_lo ? 1u : 0u);
+            const u64 v = TIP5_REDUCE96(x0, x1);
+            const int lane = i + 8 * half;
+            if (lane < 4) s[lane] = SBOX ? tip5_sbox_lut(gl_canon(v), s_lut) : gl_canon(v);
+            else s[lane] = SBOX ? tip5_sbox_pow7(v) : v;
+        }
+    }
+}
+
 template <int NVAR>
 __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *s_lut, const double *rc_lo,
                                            const double *rc_hi) {
@@ -259,6 +352,19 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
 // On exit lanes 0..3 are canonical, lanes 4..15 weak; callers canonicalise what they store.
 template <bool FIXED = false>
 __device__ __forceinline__ void tip5_permutation(u64 (&s)[TIP5_STATE], const uint8_t *s_lut) {
+#if TIP5_FUSED && TIP5_MDS_CRT
+    // S-box(0) | MDS(0) + S-box(1) | ... | MDS(3) + S-box(4) | MDS(4)
+#pragma unroll
+    for (int i = 0; i < (FIXED ? TIP5_RATE : TIP5_STATE); i++) s[i] = i < 4 ? tip5_sbox_lut(s[i], s_lut) : tip5_sbox_pow7(s[i]);
+    const double zero = *(const volatile double *)&g_tip5_zero;
+    if (FIXED) tip5_mds_sbox<TIP5_RATE, true>(s, s_lut, c_tip5_rc0f_lo, c_tip5_rc0f_hi, zero);
+#pragma unroll 1
+    for (int r = FIXED ? 1 : 0; r < TIP5_ROUNDS - 1; r++)
+        tip5_mds_sbox<TIP5_STATE, true>(s, s_lut, c_tip5_rc_lo + r * TIP5_STATE, c_tip5_rc_hi + r * TIP5_STATE, zero);
+    tip5_mds_sbox<TIP5_STATE, false>(s, s_lut, c_tip5_rc_lo + (TIP5_ROUNDS - 1) * TIP5_STATE,
+                                     c_tip5_rc_hi + (TIP5_ROUNDS - 1) * TIP5_STATE, zero);
+    return;
+#endif
     if (FIXED) tip5_round<TIP5_RATE>(s, s_lut, c_tip5_rc0f_lo, c_tip5_rc0f_hi);
 #pragma unroll 1
     for (int r = FIXED ? 1 : 0; r < TIP5_ROUNDS; r++)
