@@ -36,6 +36,9 @@ typedef uint32_t u32;
 #ifndef TF21_SHL_CARRY
 #define TF21_SHL_CARRY 1  /* carry-form canonicalisation in the q == 0 fold and z0 * EPS on the ALU in the q == 2 fold: 2^20 batch 2.97 -> 2.92 ms */
 #endif
+#ifndef TF21_SHL_Q1_CARRY
+#define TF21_SHL_Q1_CARRY 0  /* neutral: ptxas then forms z0 + z1 as LEA (ALU pipe) instead of IMAD.SHL + IMAD.IADD, the ALU count stays 7 */
+#endif
 #ifndef TF21_CANON_CARRY
 #define TF21_CANON_CARRY 1  /* carry form of the canonicalisation: one ALU instruction less per use, 2^20 batch 3.02 -> 2.96 ms */
 #endif
@@ -703,8 +706,15 @@ __device__ __forceinline__ u64 gl_shlc(u64 x, u32 one = c_gl_one) {
 #endif
     } else if constexpr (q == 1) {
         // z * 2^32 = (z0 + z1) 2^32 - (z1 + z2):  T1 = (s : -carry) < p,  T2 = z1 + z2 < 2^33
+#if TF21_SHL_Q1_CARRY
+        // the carry of z0 + z1 from the adder itself (IADD3 + IMAD.X) instead of a compare + select (ISETP + SEL): one
+        // ALU-pipe instruction less per shift by 32..63 bits
+        u32 s, c;
+        asm("add.cc.u32 %0,%2,%3;\n\taddc.u32 %1,0,0;" : "=r"(s), "=r"(c) : "r"(z0), "r"(z1));
+#else
         const u32 s = z0 + z1;
         const u32 c = (s < z0) ? 1u : 0u;
+#endif
         const u64 T1 = gl_pack(0u - c, s);
         const u64 T2 = (u64)z1 + (u64)z2;
         return gl_subl(T1, T2, one);

@@ -167,13 +167,37 @@ struct DftBfly {
     static constexpr int S = neg ? E - 96 : E;
     static constexpr bool flagged = S < 32;  // trivial twiddle or a shift that is only folded
 };
+// Running flag over the high words of a stage: "some word was 0xffffffff".
+// TF21_OPT_FLAG_MUL: the flag is the product of the (hi + 1) mod 2^32 -- zero as soon as one factor is zero -- formed
+// by one IMAD per word on the FMA-heavy pipe (the kernels are ALU-pipe bound) instead of a VIMNMX per one or two words
+// on the ALU pipe.  A product can also vanish because its factors bring 32 factors of two together (for random words
+// about once in several hundred stages): that only sends a warp through the slow path, which is always correct.
+#ifndef TF21_OPT_FLAG_MUL
+#define TF21_OPT_FLAG_MUL 0  /* measured neutral (2.319 against 2.324 ms) with chains of <= 8 factors, +2.5 % with chains of 16 (false hits in one of 32 lanes) */
+#endif
+#if TF21_OPT_FLAG_MUL
+constexpr u32 kOptFlagInit = 1u;
+__device__ __forceinline__ u32 dft_opt_flag(u32 acc, u32 hi) {
+    u32 r;
+    asm("mad.lo.u32 %0,%1,%2,%1;" : "=r"(r) : "r"(acc), "r"(hi));  // acc * (hi + 1)
+    return r;
+}
+__device__ __forceinline__ bool dft_opt_hit(u32 acc) { return acc == 0u; }
+#else
+constexpr u32 kOptFlagInit = 0u;
+__device__ __forceinline__ u32 dft_opt_flag(u32 acc, u32 hi) { return max(acc, hi); }
+__device__ __forceinline__ bool dft_opt_hit(u32 acc) { return acc == 0xffffffffu; }
+#endif
+// mx[2]: the first eight and the second eight butterflies of a stage keep separate flags (a product of more than
+// eight factors collects 32 factors of two in one of the 32 lanes of a warp far too often)
 template <bool INV, int A, int LS, int IDX, int SHLV>
-__device__ __forceinline__ void dft_opt_twiddle(u64 (&v)[1 << A], u32 one, u32 &mx) {
+__device__ __forceinline__ void dft_opt_twiddle(u64 (&v)[1 << A], u32 one, u32 (&mxs)[2]) {
     if constexpr (IDX < (1 << A) / 2) {
         using B = DftBfly<INV, A, LS, IDX>;
+        u32 &mx = mxs[TF21_OPT_FLAG_MUL ? IDX / 8 : 0];
         if constexpr (B::S != 0) v[B::ib] = gl_shlc<(B::S ? B::S : 1), (SHLV & 15), true>(v[B::ib], one);
-        if constexpr (B::flagged) mx = max(mx, (u32)(v[B::ib] >> 32));
-        dft_opt_twiddle<INV, A, LS, IDX + 1, SHLV>(v, one, mx);
+        if constexpr (B::flagged) mx = dft_opt_flag(mx, (u32)(v[B::ib] >> 32));
+        dft_opt_twiddle<INV, A, LS, IDX + 1, SHLV>(v, one, mxs);
     }
 }
 template <bool INV, int A, int LS, int IDX>
@@ -206,9 +230,10 @@ __device__ __forceinline__ void dft_opt_addsub(u64 (&v)[1 << A], u32 one) {
 template <bool INV, int A, int LS, int SHLV>
 __device__ __forceinline__ void dft_opt_stage(u64 (&v)[1 << A], u32 one) {
     if constexpr (LS <= A) {
-        u32 mx = 0;
+        u32 mx[2] = {kOptFlagInit, kOptFlagInit};
         dft_opt_twiddle<INV, A, LS, 0, SHLV>(v, one, mx);
-        if (__any_sync(0xffffffffu, mx == 0xffffffffu)) dft_opt_fix<INV, A, LS, 0>(v);
+        if (__builtin_expect(__any_sync(0xffffffffu, dft_opt_hit(mx[0]) || (TF21_OPT_FLAG_MUL && dft_opt_hit(mx[1]))), 0))
+            dft_opt_fix<INV, A, LS, 0>(v);
         dft_opt_addsub<INV, A, LS, 0, (SHLV >> 4)>(v, one);
         dft_opt_stage<INV, A, LS + 1, SHLV>(v, one);
     }
@@ -363,10 +388,11 @@ __device__ __forceinline__ void dft1024_warp(u64 (&v)[32], u64 *slice, const u64
         } else if (CANON_OUT && it) {  // last pass: canonical words straight into the outgoing tile
 #if TF21_OPT_CANON
             // optimistic: one maximum over the 32 high words; the canonicalisation only runs in a warp that saw 0xffffffff
-            u32 mx = 0;
+            // (two chains: 32 factors of a single product would bring 32 factors of two together too often)
+            u32 mx[4] = {kOptFlagInit, kOptFlagInit, kOptFlagInit, kOptFlagInit};
 #pragma unroll
-            for (int k = 0; k < 32; k++) mx = max(mx, (u32)(v[k] >> 32));
-            if (__any_sync(0xffffffffu, mx == 0xffffffffu)) {
+            for (int k = 0; k < 32; k++) mx[TF21_OPT_FLAG_MUL ? k & 3 : 0] = dft_opt_flag(mx[TF21_OPT_FLAG_MUL ? k & 3 : 0], (u32)(v[k] >> 32));
+            if (__builtin_expect(__any_sync(0xffffffffu, dft_opt_hit(mx[0]) || (TF21_OPT_FLAG_MUL && (dft_opt_hit(mx[1]) || dft_opt_hit(mx[2]) || dft_opt_hit(mx[3])))), 0)) {
 #pragma unroll
                 for (int k = 0; k < 32; k++) v[k] = gl_canonw(v[k]);
             }
@@ -563,6 +589,9 @@ __global__ void __launch_bounds__(kFastThreads, kTmaMinBlocks)
 #pragma unroll
         for (u32 q = 0; q < 1024 / kTmaBoxRows; q++)
             tma_load_3d(tile + q * kTmaBoxRows * kTmaTileCols, &src_map, ct * kTmaTileCols, q * kTmaBoxRows, slab, bar);
+        // (prefetching the tile of the CTA that will take this one's place into L2 with cp.async.bulk.prefetch.tensor,
+        // 148 ... 2960 CTAs ahead: 1.277 ... 1.313 ms against 1.278 ms -- the wait on the box loads is covered by the
+        // other resident CTAs)
     }
     // word (row 32 a + lane, column warp) = tile[off0 + 128 a]: the swizzle bit depends on the lane only
     const u32 off0 = tma_tile_word(lane, warp);
@@ -873,15 +902,42 @@ __global__ void __launch_bounds__(128) ntt_small_col_pruned_kernel(const SmallCo
         x[r] = v;
     }
     u64 *dst = a.dst + b * a.dst_array_words + off;
-    // inter-pass twiddle omega_B^(i jcol): table column, or g^i = g^d (g^M)^c from g = omega_B^jcol
-    const u64 *tcol = a.tw_full ? a.tw_full + jcol : nullptr;
-    u64 g = 0, gM = 0, gd = 1;
-    if (!tcol) {
-        g = scale_factor_l(a.tw, jcol);
-        gM = g;
+    if (!a.tw_full) {
+        // B > 2^20: no table.  With g = omega_B^jcol the inter-pass twiddle of output i = M c + d is g^d (g^M)^c, and g^d
+        // can be carried by the inputs:  out[M c + d] = (g^M)^c  sum_a (x_a h_a^d) w_NZ^(a c),  h_a = w^a g.
+        // The running values x_a h_a^d take one product per input and d, the outputs one product for c > 0:
+        // NZ + NZ - 1 products per NZ outputs (the first form -- w^(a d) from a table, a g^i chain and the product
+        // with it -- needed 3 NZ - 1).
+        const u64 g = scale_factor_l(a.tw, jcol);
+        u64 gM = g;
 #pragma unroll
         for (int k = 0; k < A - LNZ; k++) gM = gl_mul(gM, gM);
+        u64 h[NZ], P[NZ];
+        h[0] = g;
+        P[0] = 1;
+#pragma unroll
+        for (int r = 1; r < NZ; r++) {
+            h[r] = gl_mul(g, c_w64[r * (64 / NP)]);
+            P[r] = r == 1 ? gM : gl_mul(P[r - 1], gM);
+        }
+#pragma unroll 1
+        for (int d = 0; d < M; d++) {
+            u64 z[NZ];
+#pragma unroll
+            for (int r = 0; r < NZ; r++) z[r] = x[r];
+            dft_pow2<false, LNZ>(z);
+#pragma unroll
+            for (int c = 0; c < NZ; c++) {
+                const u64 v = z[brev_bits(c, LNZ)];
+                dst[(u64)(M * c + d) * a.inner_words] = c ? gl_mul(v, P[c]) : v;  // lazy words: the next pass takes any
+            }
+#pragma unroll
+            for (int r = 0; r < NZ; r++) x[r] = gl_mul(x[r], h[r]);
+        }
+        return;
     }
+    // B <= 2^20: the twiddles omega_B^(i jcol) come from the full table (consecutive threads read consecutive entries)
+    const u64 *tcol = a.tw_full + jcol;
 #pragma unroll 1
     for (int d = 0; d < M; d++) {
         u64 z[NZ];
@@ -889,20 +945,11 @@ __global__ void __launch_bounds__(128) ntt_small_col_pruned_kernel(const SmallCo
 #pragma unroll
         for (int r = 1; r < NZ; r++) z[r] = gl_mul(x[r], c_w64[((r * d) & (NP - 1)) * (64 / NP)]);
         dft_pow2<false, LNZ>(z);
-        u64 tc = gd;
 #pragma unroll
         for (int c = 0; c < NZ; c++) {
             const int i = M * c + d;
-            u64 v = z[brev_bits(c, LNZ)];
-            if (tcol) {
-                v = gl_mul(v, __ldg(tcol + (u64)i * inner_elems));
-            } else {
-                v = gl_mul(v, tc);  // i == 0: tc = 1 (or the folded scalar)
-                if (c + 1 < NZ) tc = gl_mul(tc, gM);
-            }
-            dst[(u64)i * a.inner_words] = v;
+            dst[(u64)i * a.inner_words] = gl_mul(z[brev_bits(c, LNZ)], __ldg(tcol + (u64)i * inner_elems));
         }
-        if (!tcol) gd = gl_mul(gd, g);
     }
 }
 
