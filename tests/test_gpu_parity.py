@@ -135,6 +135,36 @@ def test_bfe_ntt_matches_oracle(tf, oracle, log2n):
         assert np.array_equal(got, x)
 
 
+def sprinkled(seed, count):
+    """words whose high half is 0xffffffff in SOME lanes of a warp: the optimistic canonicalisation of the 1024-point
+    passes (csrc/ntt_fast.cuh dft_opt_stage) takes its slow path in warps where only a few lanes need it"""
+    rng = np.random.default_rng(seed)
+    a = rnd(seed, count)
+    a[rng.random(count) < 1 / 29] = np.uint64(P - 1)
+    b = np.zeros(count, dtype=np.uint64)
+    b[rng.random(count) < 1 / 61] = np.uint64(P - 1)
+    c = (rnd(seed + 1, count) & np.uint64(0xFFFFFFFF)) | np.uint64(0xFFFFFFFE00000000)
+    c[rng.random(count) < 1 / 7] = np.uint64(P - 1)
+    return [a, b, c]
+
+
+@pytest.mark.parametrize("log2n,w", [(10, 1), (10, 3), (11, 1), (12, 1), (16, 1), (20, 1), (20, 3), (21, 1)])
+def test_ntt_words_near_p_in_some_lanes(tf, oracle, log2n, w):
+    n = 1 << log2n
+    for x in sprinkled(900 + log2n + w, n * w):
+        want = x.copy()
+        assert oracle.ntt(want, w) == 0
+        got = x.copy().reshape(n, w) if w > 1 else x.copy()
+        tf.ntt(got)
+        assert np.array_equal(got.reshape(-1), want)
+        assert (got.reshape(-1) < np.uint64(P)).all()
+        want_i = x.copy()
+        oracle.intt(want_i, w)
+        got_i = x.copy().reshape(n, w) if w > 1 else x.copy()
+        tf.intt(got_i)
+        assert np.array_equal(got_i.reshape(-1), want_i)
+
+
 @pytest.mark.parametrize("log2n", list(range(0, 23)))
 def test_xfe_ntt_matches_oracle(tf, oracle, log2n):
     n = 1 << log2n
