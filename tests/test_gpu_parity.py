@@ -523,6 +523,50 @@ def test_config1_full_batch_256_x_2_20(tf, oracle):
     assert np.array_equal(x, orig)
 
 
+
+@pytest.mark.parametrize("log2n,width,batch", [(20, 1, 25), (21, 3, 3), (24, 1, 2), (12, 1, 5000)])
+def test_pageable_host_slices_go_through_the_pinned_ring(tf, oracle, log2n, width, batch):
+    """A plain numpy array is pageable memory, like the reference caller's Vec<BFieldElement> (ntt.rs:67,109): tf21_ntt /
+    tf21_intt move it through the pinned staging ring of csrc/host_stage.cuh (whole chunks, a ragged last chunk, arrays
+    larger than a chunk, many small arrays per chunk).  Bit-exact against the oracle, and against the driver-staged copy
+    path (TF21_NO_STAGE_RING=1) the ring replaces."""
+    api = importlib.import_module("twenty-first_b200.api")
+    n = 1 << log2n
+    x = rnd(0x7700 + log2n + batch, n * width * batch)
+    want = x.copy()
+    assert oracle.ntt_batch(want, n, width, batch, False) == 0
+    got = x.copy()
+    api.ntt_batch(got, n, width, False)
+    assert np.array_equal(got, want)
+    os.environ["TF21_NO_STAGE_RING"] = "1"
+    try:
+        direct = x.copy()
+        api.ntt_batch(direct, n, width, False)
+    finally:
+        del os.environ["TF21_NO_STAGE_RING"]
+    assert np.array_equal(direct, want)
+    api.ntt_batch(got, n, width, True)
+    assert np.array_equal(got, x)
+
+
+def test_host_merkle_build_writes_the_leaf_half_on_the_host(tf, oracle):
+    """tf21_merkle_build on pageable slices: leaves through the ring, inner nodes back through the ring, the leaf half of
+    the node array copied on the host (merkle_tree.rs:426) -- every node against the oracle, with the driver-staged path
+    next to it."""
+    n = 1 << 21
+    leafs = rnd(0x7800, 5 * n)
+    rc, want = oracle.merkle_par_new(leafs)
+    assert rc == 0
+    tree = tf.MerkleTree.par_new(leafs.reshape(n, 5))
+    assert np.array_equal(tree.nodes.reshape(-1), want)
+    os.environ["TF21_NO_STAGE_RING"] = "1"
+    try:
+        tree2 = tf.MerkleTree.par_new(leafs.reshape(n, 5))
+    finally:
+        del os.environ["TF21_NO_STAGE_RING"]
+    assert np.array_equal(tree2.nodes.reshape(-1), want)
+
+
 def test_config2_merkle_2_24_full_node_array(tf, oracle):
     """BASELINE configs[2] at full size: every one of the 2^25 node digests against the oracle."""
     n = 1 << 24

@@ -8,6 +8,7 @@
 #include <thread>
 #include "ntt_fast.cuh"
 #include "tip5_kernels.cuh"
+#include "host_stage.cuh"
 
 using namespace tf21;
 
@@ -210,6 +211,11 @@ static int split_locked(DeviceTables &t, u64 g, u64 c0, u64 count, ScaleTab *out
     return 0;
 }
 
+static u64 l2_group_cols() {
+    const char *e = getenv("TF21_L2_GROUP");
+    return e ? (u64)strtoull(e, nullptr, 10) : 0;
+}
+
 static int ntt_run_locked(DeviceTables &t, const u64 *src, u64 n_in, u64 *dst, u64 n, u32 w, u64 batch, int inverse,
                           ScaleTab pre, ScaleTab post, u64 post_scalar, cudaStream_t st) {
     if (n <= 1) {  // identity transform (ntt.rs:178-181 returns early; len 1 has no stages)
@@ -220,6 +226,41 @@ static int ntt_run_locked(DeviceTables &t, const u64 *src, u64 n_in, u64 *dst, u
     }
     int dev;
     TF21_TRY(current_device(&dev));
+    // Column-group schedule (TF21_L2_GROUP = columns per group): the batch is cut into groups whose inter-pass scratch
+    // (group * n * w * 8 bytes) fits the 126 MB L2, and the groups alternate between two side streams, so that the
+    // tail wave of one group's pass overlaps the other group's kernels while the scratch written by the column
+    // pass is still L2-resident when the row pass reads it.  Scratch shrinks from the batch to two groups.
+    const u64 group = l2_group_cols();
+    if (group > 0 && ilog2_u64(n) > kNttMaxLogPass && batch >= 4 * group) {
+        cudaStream_t ss[2] = {nullptr, nullptr};
+        cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+        int rc = 0;
+        for (int i = 0; i < 3 && rc == 0; i++)
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess)
+                rc = cuda_fail(cudaGetLastError(), "cudaEventCreate", __LINE__);
+        if (rc == 0 && cudaEventRecord(ev[2], st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaEventRecord", __LINE__);
+        for (int i = 0; i < 2 && rc == 0; i++)
+            if (cudaStreamCreateWithFlags(&ss[i], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamWaitEvent(ss[i], ev[2], 0) != cudaSuccess)
+                rc = cuda_fail(cudaGetLastError(), "group stream", __LINE__);
+        if (rc == 0) {
+            Scratch s0(ss[0]), s1(ss[1]);
+            rc = s0.alloc(n * w * group);
+            if (rc == 0) rc = s1.alloc(n * w * group);
+            for (u64 b0 = 0, g = 0; b0 < batch && rc == 0; b0 += group, g++) {
+                const u64 cnt = batch - b0 < group ? batch - b0 : group;
+                rc = ntt_run(t, dev, src + b0 * n_in * w, n_in, dst + b0 * n * w, n, w, cnt, inverse, pre, post, post_scalar,
+                             (g & 1) ? s1.p : s0.p, ss[g & 1]);
+            }
+        }
+        for (int i = 0; i < 2; i++) {
+            if (ss[i] && ev[i] && cudaEventRecord(ev[i], ss[i]) == cudaSuccess) cudaStreamWaitEvent(st, ev[i], 0);
+            if (ss[i]) cudaStreamDestroy(ss[i]);  // released once its work has drained
+        }
+        for (int i = 0; i < 3; i++)
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        return rc;
+    }
     Scratch scratch(st);
     if (ilog2_u64(n) > kNttMaxLogPass) TF21_TRY(scratch.alloc(n * w * batch));
     return ntt_run(t, dev, src, n_in, dst, n, w, batch, inverse, pre, post, post_scalar, scratch.p, st);
@@ -260,6 +301,7 @@ int tf21_device_count(void) {
 }
 
 int tf21_shutdown(void) {
+    stage_ring_free_all();
     {
         std::lock_guard<std::mutex> nlock(g_nccl_mutex);
         for (auto &kv : g_nccl_comms)
@@ -452,6 +494,7 @@ static int host_ntt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch, 
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     u64 *bufs[3] = {nullptr, nullptr, nullptr};
     int rc = 0;
+    const bool pageable = host_ptr_is_pageable(data);
     auto cleanup = [&]() {
         for (int i = 0; i < n_streams; i++) {
             if (streams[i]) {
@@ -466,7 +509,31 @@ static int host_ntt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch, 
             cudaMallocAsync((void **)&bufs[i], chunk_arrays * array_words * sizeof(u64), streams[i]) != cudaSuccess)
             rc = cuda_fail(cudaGetLastError(), "host_ntt staging", __LINE__);
     }
-    for (u64 c = 0; c < n_chunks && rc == 0; c++) {
+    if (pageable && rc == 0) {
+        // a plain Vec / malloc slice: through the pinned ring (host_stage.cuh), one staged call at a time
+        StagedPass sp;
+        rc = current_device(&sp.dev);
+        if (rc == 0) rc = stage_ring_get(sp.dev, &sp.ring);
+        if (rc == 0) {
+            std::lock_guard<std::mutex> stage_lock(sp.ring->busy);
+            sp.host_in = (const char *)data;
+            sp.host_out = (char *)data;
+            for (u64 c = 0; c <= n_chunks; c++) {
+                const u64 a0 = c * chunk_arrays < batch ? c * chunk_arrays : batch;
+                sp.chunk_off.push_back((size_t)(a0 * array_words * sizeof(u64)));
+            }
+            sp.n_lanes = n_streams;
+            sp.streams = streams;
+            sp.dev_bufs = (char **)bufs;
+            sp.compute = [&](size_t c, int lane) {
+                const u64 a0 = (u64)c * chunk_arrays;
+                const u64 cnt = (a0 + chunk_arrays <= batch) ? chunk_arrays : batch - a0;
+                return tf21_ntt_dev(bufs[lane], n, width, cnt, inverse, (tf21_stream_t)streams[lane]);
+            };
+            rc = sp.run();
+        }
+    }
+    for (u64 c = 0; c < n_chunks && rc == 0 && !pageable; c++) {
         const int si = (int)(c % (u64)n_streams);
         const u64 a0 = c * chunk_arrays;
         const u64 cnt = (a0 + chunk_arrays <= batch) ? chunk_arrays : batch - a0;
@@ -570,9 +637,9 @@ int tf21_coset_evaluate(const uint64_t *coeffs, uint64_t n_coeffs, uint32_t widt
     DevBuf in, outb;
     TF21_TRY(in.alloc(live * width));
     TF21_TRY(outb.alloc(order * width));
-    if (live) TF21_CUDA(cudaMemcpy(in.p, coeffs, live * width * sizeof(u64), cudaMemcpyHostToDevice));
+    if (live) TF21_TRY(copy_h2d(in.p, coeffs, live * width * sizeof(u64), nullptr));
     TF21_TRY(tf21_coset_evaluate_dev(in.p, live, width, offset_raw, order, outb.p, nullptr));
-    TF21_CUDA(cudaMemcpy(out, outb.p, order * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, outb.p, order * width * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -583,9 +650,9 @@ int tf21_coset_interpolate(const uint64_t *values, uint64_t n, uint32_t width, u
     DevBuf in, outb;
     TF21_TRY(in.alloc(n * width));
     TF21_TRY(outb.alloc(n * width));
-    TF21_CUDA(cudaMemcpy(in.p, values, n * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(in.p, values, n * width * sizeof(u64), nullptr));
     TF21_TRY(tf21_coset_interpolate_dev(in.p, n, width, offset_raw, outb.p, nullptr));
-    TF21_CUDA(cudaMemcpy(coeffs_out, outb.p, n * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(coeffs_out, outb.p, n * width * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -597,9 +664,9 @@ int tf21_coset_lde(const uint64_t *values, uint64_t n_in, uint64_t offset_in_raw
     DevBuf in, outb;
     TF21_TRY(in.alloc(n_in * width));
     TF21_TRY(outb.alloc(n_out * width));
-    TF21_CUDA(cudaMemcpy(in.p, values, n_in * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(in.p, values, n_in * width * sizeof(u64), nullptr));
     TF21_TRY(tf21_coset_lde_dev(in.p, n_in, offset_in_raw, n_out, offset_out_raw, width, outb.p, nullptr));
-    TF21_CUDA(cudaMemcpy(out, outb.p, n_out * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, outb.p, n_out * width * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -651,9 +718,9 @@ int tf21_poly_square(const uint64_t *a, uint64_t n_a, uint32_t width, uint64_t *
     DevBuf da, dout;
     TF21_TRY(da.alloc(n_a * width));
     TF21_TRY(dout.alloc(len * width));
-    TF21_CUDA(cudaMemcpy(da.p, a, n_a * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(da.p, a, n_a * width * sizeof(u64), nullptr));
     TF21_TRY(tf21_poly_square_dev(da.p, n_a, width, dout.p, nullptr));
-    TF21_CUDA(cudaMemcpy(out, dout.p, len * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, dout.p, len * width * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -666,10 +733,10 @@ int tf21_poly_mul(const uint64_t *a, uint64_t n_a, const uint64_t *b, uint64_t n
     TF21_TRY(da.alloc(n_a * width));
     TF21_TRY(db.alloc(n_b * width));
     TF21_TRY(dout.alloc(len * width));
-    TF21_CUDA(cudaMemcpy(da.p, a, n_a * width * sizeof(u64), cudaMemcpyHostToDevice));
-    TF21_CUDA(cudaMemcpy(db.p, b, n_b * width * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(da.p, a, n_a * width * sizeof(u64), nullptr));
+    TF21_TRY(copy_h2d(db.p, b, n_b * width * sizeof(u64), nullptr));
     TF21_TRY(tf21_poly_mul_dev(da.p, n_a, db.p, n_b, width, dout.p, nullptr));
-    TF21_CUDA(cudaMemcpy(out, dout.p, len * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, dout.p, len * width * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -703,8 +770,8 @@ int tf21_poly_reduce_by_ntt_friendly_modulus(const uint64_t *coeffs, uint64_t n_
     TF21_TRY(win[0].alloc(domain_length * w));
     TF21_TRY(win[1].alloc(domain_length * w));
     TF21_TRY(prod.alloc(domain_length * w));
-    TF21_CUDA(cudaMemcpy(dc.p, coeffs, n_coeffs * w * sizeof(u64), cudaMemcpyHostToDevice));
-    TF21_CUDA(cudaMemcpy(dshift.p, shift_ntt, domain_length * w * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(dc.p, coeffs, n_coeffs * w * sizeof(u64), nullptr));
+    TF21_TRY(copy_h2d(dshift.p, shift_ntt, domain_length * w * sizeof(u64), nullptr));
     // working_window = coefficients[range_start..] zero-padded to chunk + tail (:1103-1109)
     TF21_CUDA(cudaMemsetAsync(win[0].p, 0, domain_length * w * sizeof(u64), st));
     if (range_start < n_coeffs)
@@ -730,7 +797,7 @@ int tf21_poly_reduce_by_ntt_friendly_modulus(const uint64_t *coeffs, uint64_t n_
                     prod.p, chunk * w, domain_length * w, win[cur ^ 1].p);
         cur ^= 1;
     }
-    TF21_CUDA(cudaMemcpy(out, win[cur].p, domain_length * w * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, win[cur].p, domain_length * w * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -763,8 +830,8 @@ int tf21_poly_clean_divide(const uint64_t *a, uint64_t n_a, const uint64_t *b, u
     TF21_TRY(ea.alloc(order));
     TF21_TRY(eb.alloc(order));
     TF21_TRY(flag.alloc(1));
-    TF21_CUDA(cudaMemcpy(da.p, a, n_a * sizeof(u64), cudaMemcpyHostToDevice));
-    TF21_CUDA(cudaMemcpy(db.p, b, n_b * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(da.p, a, n_a * sizeof(u64), nullptr));
+    TF21_TRY(copy_h2d(db.p, b, n_b * sizeof(u64), nullptr));
     u64 offset = 7;  // BFieldElement::generator()
     for (int attempt = 0; attempt < 8; attempt++, offset = hgl_mul(offset, 7)) {
         const u64 offset_raw = hgl_to_raw(offset);
@@ -774,10 +841,10 @@ int tf21_poly_clean_divide(const uint64_t *a, uint64_t n_a, const uint64_t *b, u
         TF21_LAUNCH(pointwise_divide_kernel, grid_for(order, 256), 256, 0, (cudaStream_t) nullptr, ea.p, eb.p, order,
                     (u32 *)flag.p);
         u64 hit = 0;
-        TF21_CUDA(cudaMemcpy(&hit, flag.p, sizeof(u64), cudaMemcpyDeviceToHost));
+        TF21_TRY(copy_d2h(&hit, flag.p, sizeof(u64), nullptr));
         if (hit) continue;  // the coset contains a root of the divisor: next offset
         TF21_TRY(tf21_coset_interpolate_dev(ea.p, order, 1, offset_raw, eb.p, nullptr));
-        TF21_CUDA(cudaMemcpy(q_out, eb.p, len * sizeof(u64), cudaMemcpyDeviceToHost));
+        TF21_TRY(copy_d2h(q_out, eb.p, len * sizeof(u64), nullptr));
         return 0;
     }
     return TF21_E_BAD_ARG;
@@ -850,10 +917,10 @@ int tf21_batch_coset_extrapolate(uint64_t offset_raw, uint64_t codeword_length, 
     const u64 words = codeword_length * width * n_codewords;
     TF21_TRY(dc.alloc(words));
     TF21_TRY(dout.alloc(n_codewords * n_points * width));
-    TF21_CUDA(cudaMemcpy(dc.p, codewords, words * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(dc.p, codewords, words * sizeof(u64), nullptr));
     TF21_TRY(tf21_batch_coset_extrapolate_dev(offset_raw, codeword_length, dc.p, n_codewords, width, points, n_points,
                                               dout.p, nullptr));
-    TF21_CUDA(cudaMemcpy(out, dout.p, n_codewords * n_points * width * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, dout.p, n_codewords * n_points * width * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -896,11 +963,11 @@ int tf21_tip5_sample_indices(uint64_t *state, uint32_t upper_bound, uint64_t num
     DevBuf ds, dout;
     TF21_TRY(ds.alloc(16));
     TF21_TRY(dout.alloc((num_indices + 1) / 2));
-    TF21_CUDA(cudaMemcpy(ds.p, state, 16 * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(ds.p, state, 16 * sizeof(u64), nullptr));
     TF21_LAUNCH(tip5_sample_indices_kernel, 1, 32, 0, (cudaStream_t) nullptr, ds.p, upper_bound, num_indices,
                 hgl_inv(GL_EPS), (u32 *)dout.p);
-    TF21_CUDA(cudaMemcpy(out, dout.p, num_indices * sizeof(u32), cudaMemcpyDeviceToHost));
-    TF21_CUDA(cudaMemcpy(state, ds.p, 16 * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, dout.p, num_indices * sizeof(u32), nullptr));
+    TF21_TRY(copy_d2h(state, ds.p, 16 * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -909,9 +976,9 @@ int tf21_tip5_permute(uint64_t *states, uint64_t count) {
     if (!states) return TF21_E_BAD_ARG;
     DevBuf b;
     TF21_TRY(b.alloc(16 * count));
-    TF21_CUDA(cudaMemcpy(b.p, states, 16 * count * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(b.p, states, 16 * count * sizeof(u64), nullptr));
     TF21_TRY(tf21_tip5_permute_dev(b.p, count, nullptr));
-    TF21_CUDA(cudaMemcpy(states, b.p, 16 * count * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(states, b.p, 16 * count * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -921,9 +988,9 @@ int tf21_tip5_hash_10(const uint64_t *in, uint64_t count, uint64_t *out) {
     DevBuf bi, bo;
     TF21_TRY(bi.alloc(10 * count));
     TF21_TRY(bo.alloc(5 * count));
-    TF21_CUDA(cudaMemcpy(bi.p, in, 10 * count * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(bi.p, in, 10 * count * sizeof(u64), nullptr));
     TF21_TRY(tf21_tip5_hash_10_dev(bi.p, count, bo.p, nullptr));
-    TF21_CUDA(cudaMemcpy(out, bo.p, 5 * count * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, bo.p, 5 * count * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -937,9 +1004,9 @@ int tf21_tip5_hash_rows(const uint64_t *rows, uint64_t row_len, uint64_t n_rows,
     DevBuf bi, bo;
     TF21_TRY(bi.alloc(row_len * n_rows));
     TF21_TRY(bo.alloc(5 * n_rows));
-    if (row_len) TF21_CUDA(cudaMemcpy(bi.p, rows, row_len * n_rows * sizeof(u64), cudaMemcpyHostToDevice));
+    if (row_len) TF21_TRY(copy_h2d(bi.p, rows, row_len * n_rows * sizeof(u64), nullptr));
     TF21_TRY(tf21_tip5_hash_rows_dev(bi.p, row_len, n_rows, bo.p, nullptr));
-    TF21_CUDA(cudaMemcpy(out, bo.p, 5 * n_rows * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, bo.p, 5 * n_rows * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -1069,10 +1136,10 @@ int tf21_merkle_authentication_structure_from_leafs(const uint64_t *leafs, uint6
     TF21_TRY(bl.alloc(5 * n_leafs));
     TF21_TRY(bn.alloc(10 * n_leafs));
     TF21_TRY(bo.alloc(5 * c));
-    TF21_CUDA(cudaMemcpy(bl.p, leafs, 5 * n_leafs * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(bl.p, leafs, 5 * n_leafs * sizeof(u64), nullptr));
     TF21_TRY(tf21_merkle_build_dev(bl.p, n_leafs, bn.p, nullptr));
     TF21_TRY(tf21_merkle_authentication_structure_dev(bn.p, n_leafs, leaf_indices, n_indices, bo.p, c, &c, nullptr));
-    TF21_CUDA(cudaMemcpy(out, bo.p, 5 * c * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, bo.p, 5 * c * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -1111,9 +1178,9 @@ int tf21_mmr_peaks_from_leafs(const uint64_t *leafs, uint64_t n_leafs, uint64_t 
     DevBuf bl, bp;
     TF21_TRY(bl.alloc(5 * n_leafs));
     TF21_TRY(bp.alloc(5 * 64));
-    TF21_CUDA(cudaMemcpy(bl.p, leafs, 5 * n_leafs * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(bl.p, leafs, 5 * n_leafs * sizeof(u64), nullptr));
     TF21_TRY(tf21_mmr_peaks_from_leafs_dev(bl.p, n_leafs, bp.p, n_peaks, nullptr));
-    TF21_CUDA(cudaMemcpy(peaks_out, bp.p, 5 * *n_peaks * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(peaks_out, bp.p, 5 * *n_peaks * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -1133,9 +1200,9 @@ int tf21_mmr_bag_peaks(const uint64_t *peaks, uint64_t n_peaks, uint64_t leaf_co
     DevBuf bp, bo;
     TF21_TRY(bp.alloc(5 * n_peaks));
     TF21_TRY(bo.alloc(5));
-    if (n_peaks) TF21_CUDA(cudaMemcpy(bp.p, peaks, 5 * n_peaks * sizeof(u64), cudaMemcpyHostToDevice));
+    if (n_peaks) TF21_TRY(copy_h2d(bp.p, peaks, 5 * n_peaks * sizeof(u64), nullptr));
     TF21_TRY(tf21_mmr_bag_peaks_dev(bp.p, n_peaks, leaf_count, bo.p, nullptr));
-    TF21_CUDA(cudaMemcpy(out, bo.p, 5 * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(out, bo.p, 5 * sizeof(u64), nullptr));
     return 0;
 }
 
@@ -1334,10 +1401,19 @@ int tf21_merkle_build(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_o
     DevBuf bl, bn;
     TF21_TRY(bl.alloc(5 * n_leafs));
     TF21_TRY(bn.alloc(10 * n_leafs));
-    TF21_CUDA(cudaMemcpy(bl.p, leafs, 5 * n_leafs * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(bl.p, leafs, 5 * n_leafs * sizeof(u64), nullptr));
     TF21_TRY(tf21_merkle_build_dev(bl.p, n_leafs, bn.p, nullptr));
-    TF21_CUDA(cudaMemcpy(nodes_out, bn.p, 10 * n_leafs * sizeof(u64), cudaMemcpyDeviceToHost));
-    return 0;
+    // nodes[n .. 2n) is a copy of the caller's own leaves (merkle_tree.rs:426): it is written on the host while the
+    // device hashes, and only the inner nodes cross PCIe
+    std::thread leaf_copy;
+    const bool overlap = (leafs + 5 * n_leafs <= nodes_out || nodes_out + 10 * n_leafs <= leafs) && n_leafs >= (1u << 16);
+    if (overlap)
+        leaf_copy = std::thread([=] { parallel_memcpy(nodes_out + 5 * n_leafs, leafs, 5 * n_leafs * sizeof(u64)); });
+    else
+        memmove(nodes_out + 5 * n_leafs, leafs, 5 * n_leafs * sizeof(u64));
+    const int rc = copy_d2h(nodes_out, bn.p, 5 * n_leafs * sizeof(u64), nullptr);
+    if (leaf_copy.joinable()) leaf_copy.join();
+    return rc;
 }
 
 int tf21_merkle_root(const uint64_t *leafs, uint64_t n_leafs, uint64_t root_out[5]) {
@@ -1346,9 +1422,9 @@ int tf21_merkle_root(const uint64_t *leafs, uint64_t n_leafs, uint64_t root_out[
     DevBuf bl, br;
     TF21_TRY(bl.alloc(5 * n_leafs));
     TF21_TRY(br.alloc(5));
-    TF21_CUDA(cudaMemcpy(bl.p, leafs, 5 * n_leafs * sizeof(u64), cudaMemcpyHostToDevice));
+    TF21_TRY(copy_h2d(bl.p, leafs, 5 * n_leafs * sizeof(u64), nullptr));
     TF21_TRY(tf21_merkle_root_dev(bl.p, n_leafs, br.p, nullptr));
-    TF21_CUDA(cudaMemcpy(root_out, br.p, 5 * sizeof(u64), cudaMemcpyDeviceToHost));
+    TF21_TRY(copy_d2h(root_out, br.p, 5 * sizeof(u64), nullptr));
     return 0;
 }
 
