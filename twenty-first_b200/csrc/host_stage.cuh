@@ -120,6 +120,15 @@ inline bool host_ptr_is_pageable(const void *p) {
     return attr.type == cudaMemoryTypeUnregistered;
 }
 
+// bytes per piece (<= slot size); TF21_STAGE_PIECE_KB for A/B runs
+inline size_t stage_piece_bytes() {
+    if (const char *e = getenv("TF21_STAGE_PIECE_KB")) {
+        const size_t v = (size_t)strtoull(e, nullptr, 10) << 10;
+        if (v >= (64u << 10) && v <= kStageSlotBytes) return v & ~(size_t)4095;
+    }
+    return kStageSlotBytes;
+}
+
 inline int stage_threads() {
     if (const char *e = getenv("TF21_STAGE_THREADS")) {
         const int v = atoi(e);
@@ -173,10 +182,11 @@ struct StagedPass {
         for (size_t c = 0; c < n_chunks; c++) {
             chunk_first_piece[c] = piece_chunk.size();
             const size_t bytes = chunk_off[c + 1] - chunk_off[c];
-            for (size_t o = 0; o < bytes; o += kStageSlotBytes) {
+            const size_t piece = stage_piece_bytes();
+            for (size_t o = 0; o < bytes; o += piece) {
                 piece_chunk.push_back(c);
                 piece_off.push_back(o);
-                piece_len.push_back(bytes - o < kStageSlotBytes ? bytes - o : kStageSlotBytes);
+                piece_len.push_back(bytes - o < piece ? bytes - o : piece);
             }
         }
         chunk_first_piece[n_chunks] = piece_chunk.size();

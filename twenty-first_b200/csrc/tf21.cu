@@ -464,14 +464,16 @@ int tf21_ntt_dev(uint64_t *d_data, uint64_t n, uint32_t width, uint64_t batch, i
 }
 
 // host staging helper: device buffer with H2D on construction side and D2H on demand
+// (stream-ordered on the legacy stream the host entry points work on: the pool keeps the memory cached between calls,
+// a cudaMalloc / cudaFree pair of 2 GB costs milliseconds and a device-wide synchronisation)
 struct DevBuf {
     u64 *p = nullptr;
     int alloc(u64 words) {
-        TF21_CUDA(cudaMalloc((void **)&p, (words ? words : 1) * sizeof(u64)));
+        TF21_CUDA(cudaMallocAsync((void **)&p, (words ? words : 1) * sizeof(u64), nullptr));
         return 0;
     }
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, nullptr);
     }
 };
 

@@ -198,6 +198,46 @@ __global__ void __launch_bounds__(kMerkleTailThreads) merkle_tail_kernel(u64 *no
     }
 }
 
+// Top of a Merkle tree in ONE persistent kernel: every level with cnt = first_cnt, first_cnt/2, ..., 1 nodes, the
+// levels separated by a grid-wide barrier instead of a kernel boundary.  One CTA per SM (cooperative launch: all CTAs
+// are resident, so the spin barrier cannot deadlock), 16 lanes per hash, consecutive hashes on different SMs so that a
+// level with few nodes runs one 16-lane group per SM at the lowest latency the permutation has.  Replaces ~16 launches
+// (two thread-per-hash levels, five cooperative levels, the single-CTA tail) of the level-batched build
+// (sequentially_fill_tree, merkle_tree.rs:216-222): each level costs the latency of one cooperative hash plus a barrier
+// instead of a launch, which is what a 2^16-leaf tree (a FRI round) consists of.
+// Children digests were written by other SMs earlier in this kernel: they are read with ld.global.cg (L2), never
+// through the non-coherent path.  bar: a zeroed u32, counts arrivals (monotonic over the levels).
+constexpr int kMerkleTopThreads = 1024;
+__global__ void __launch_bounds__(kMerkleTopThreads, 1) merkle_top_kernel(u64 *nodes, u32 first_cnt, u32 *bar) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ u64 s_rc[TIP5_ROUNDS * TIP5_STATE];
+    tip5_coop_setup(s_lut, s_rc);
+    __syncthreads();
+    const u32 lane16 = threadIdx.x & 15;
+    const u32 g = (threadIdx.x >> 4) * gridDim.x + blockIdx.x;
+    const u32 n_groups = gridDim.x * (kMerkleTopThreads / 16);
+    u32 target = 0;
+    for (u32 cnt = first_cnt; cnt >= 1; cnt >>= 1) {
+        for (u32 i = g; i < cnt; i += n_groups) {
+            const u64 *in = nodes + 10ull * (cnt + i);
+            u64 s = lane16 < TIP5_RATE ? __ldcg(in + lane16) : TIP5_RAW_ONE;
+            s = tip5_permutation_coop(s, lane16, s_lut, s_rc);
+            if (lane16 < TIP5_DIGEST) __stcg(nodes + 5ull * (cnt + i) + lane16, s);
+        }
+        if (cnt == 1) break;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();  // this CTA's digests are visible device-wide before its arrival is
+            atomicAdd(bar, 1u);
+            target += gridDim.x;
+            while (*(volatile u32 *)bar < target) {
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
 // Tip5::hash_varlen over rows (tip5/mod.rs:617-623, sponge.rs:41-56): one row per thread,
 // overwrite-mode absorb of 10-word chunks, padding 1,0,.. always present.  Element k of row i is
 // data[i * row_stride + k * elem_stride]: (row_len, 1) for a row-major matrix, (1, column stride)
@@ -384,9 +424,61 @@ inline int launch_hash_rows(const u64 *d_data, u64 row_len, u64 n_rows, u64 row_
 constexpr u32 kMerkleTailCnt = 128;    // levels with <= this many nodes are finished by one CTA
 
 // fills nodes[1..n) given nodes[n..2n) (sequentially_fill_tree, merkle_tree.rs:216-222, level-batched)
+#ifndef TF21_MERKLE_TOP_CNT
+#define TF21_MERKLE_TOP_CNT 8192
+#endif
+// levels with <= this many nodes are finished by merkle_top_kernel (0: never); TF21_MERKLE_TOP_CNT in the environment
+// overrides the default for A/B runs
+inline u64 merkle_top_cnt() {
+    static const u64 v = [] {
+        const char *e = getenv("TF21_MERKLE_TOP_CNT");
+        return e ? (u64)strtoull(e, nullptr, 10) : (u64)TF21_MERKLE_TOP_CNT;
+    }();
+    return v;
+}
+
+// one cooperative launch for the levels cnt, cnt/2, ..., 1; returns 1 when the device refuses a cooperative grid
+// (the caller then takes the level-by-level path), < 0 never, TF21 error codes otherwise
+inline int launch_merkle_top(u64 *d_nodes, u64 cnt, cudaStream_t st) {
+    int dev = 0, sms = 0, coop = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || !coop || sms <= 0) {
+        cudaGetLastError();
+        return 1;
+    }
+    u32 *bar = nullptr;
+    TF21_CUDA(cudaMallocAsync((void **)&bar, sizeof(u32), st));
+    cudaMemsetAsync(bar, 0, sizeof(u32), st);
+    // no more CTAs than the first level has 16-lane groups for (a 2^8-leaf tree does not need 148 CTAs at a barrier)
+    u64 grid = (cnt + kMerkleTopThreads / 16 - 1) / (kMerkleTopThreads / 16);
+    if (grid > (u64)sms) grid = (u64)sms;
+    u32 first_cnt = (u32)cnt;
+    void *args[] = {(void *)&d_nodes, (void *)&first_cnt, (void *)&bar};
+    ProfRec pr;
+    const bool prof = g_prof_enabled.load(std::memory_order_relaxed);
+    if (prof) prof_begin("merkle_top_kernel", st, &pr);
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)merkle_top_kernel, dim3((unsigned)grid),
+                                                      dim3(kMerkleTopThreads), args, 0, st);
+    if (prof) prof_end(st, &pr);
+    cudaFreeAsync(bar, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+        cudaGetLastError();
+        return 1;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "merkle_top_kernel", __LINE__);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 inline int launch_merkle_levels(u64 *d_nodes, u64 n_leafs, cudaStream_t st) {
     u64 cnt = n_leafs / 2;
+    const u64 top = merkle_top_cnt();
     while (cnt > kMerkleTailCnt) {
+        if (cnt <= top) {
+            const int rc = launch_merkle_top(d_nodes, cnt, st);
+            if (rc == 0) return 0;
+            if (rc != 1) return rc;
+        }
         if (cnt > kMerkleCoopCnt) {
             TF21_TRY(launch_hash10(d_nodes + 10 * cnt, cnt, d_nodes + 5 * cnt, st));
         } else {
