@@ -256,8 +256,12 @@ struct StagedPass {
         const size_t n_chunks = chunk_off.size() - 1;
         const int nt = stage_threads();
         std::vector<std::thread> workers;
-        for (int t = 0; t < nt && host_in; t++) workers.emplace_back([this] { in_worker(); });
-        for (int t = 0; t < nt && host_out; t++) workers.emplace_back([this] { out_worker(); });
+        try {  // nothing may unwind across the C ABI: a thread the OS refuses becomes an error code
+            for (int t = 0; t < nt && host_in; t++) workers.emplace_back([this] { in_worker(); });
+            for (int t = 0; t < nt && host_out; t++) workers.emplace_back([this] { out_worker(); });
+        } catch (...) {
+            fail(TF21_E_ALLOC);
+        }
         size_t out_seq = 0;
         for (size_t c = 0; c < n_chunks; c++) {
             const int lane = (int)(c % (size_t)n_lanes);
@@ -327,12 +331,15 @@ inline void parallel_memcpy(void *dst, const void *src, size_t bytes) {
     }
     std::vector<std::thread> th;
     const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
-    for (int t = 0; t < nt; t++) {
-        const size_t o = (size_t)t * per;
-        if (o >= bytes) break;
-        const size_t len = bytes - o < per ? bytes - o : per;
-        th.emplace_back([=] { stage_copy((char *)dst + o, (const char *)src + o, len); });
+    size_t done = 0;
+    try {
+        for (int t = 0; t + 1 < nt && done + per < bytes; t++, done += per) {
+            const size_t o = done;
+            th.emplace_back([=] { stage_copy((char *)dst + o, (const char *)src + o, per); });
+        }
+    } catch (...) {  // fewer helpers than asked for: this thread copies what is left
     }
+    stage_copy((char *)dst + done, (const char *)src + done, bytes - done);
     for (auto &x : th) x.join();
 }
 

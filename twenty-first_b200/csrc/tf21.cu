@@ -1409,10 +1409,15 @@ int tf21_merkle_build(const uint64_t *leafs, uint64_t n_leafs, uint64_t *nodes_o
     // device hashes, and only the inner nodes cross PCIe
     std::thread leaf_copy;
     const bool overlap = (leafs + 5 * n_leafs <= nodes_out || nodes_out + 10 * n_leafs <= leafs) && n_leafs >= (1u << 16);
-    if (overlap)
-        leaf_copy = std::thread([=] { parallel_memcpy(nodes_out + 5 * n_leafs, leafs, 5 * n_leafs * sizeof(u64)); });
-    else
-        memmove(nodes_out + 5 * n_leafs, leafs, 5 * n_leafs * sizeof(u64));
+    bool started = false;
+    if (overlap) {
+        try {
+            leaf_copy = std::thread([=] { parallel_memcpy(nodes_out + 5 * n_leafs, leafs, 5 * n_leafs * sizeof(u64)); });
+            started = true;
+        } catch (...) {
+        }
+    }
+    if (!started) memmove(nodes_out + 5 * n_leafs, leafs, 5 * n_leafs * sizeof(u64));
     const int rc = copy_d2h(nodes_out, bn.p, 5 * n_leafs * sizeof(u64), nullptr);
     if (leaf_copy.joinable()) leaf_copy.join();
     return rc;
