@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+{
+for lib in libtf21.so libtf21_opt.so; do echo "== $lib"; TF21_LIB=$PWD/twenty-first_b200/$lib SWEEP_SIZES=15,16,17,18,26,27 timeout 600 python tools/size_sweep.py 2>&1 | grep "w="; done
+TF21_LIB=$PWD/twenty-first_b200/libtf21_opt.so timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "bfe_ntt_matches_oracle or xfe_ntt_matches_oracle or batched_ntt or four_pass or near_p" 2>&1 | tail -2
+} > gpurun_out/ab_run18.log 2>&1

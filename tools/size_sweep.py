@@ -8,7 +8,7 @@ dev.init(0)
 HBM = 6448.1e9
 total_log = int(os.environ.get("TOTAL_LOG", "27"))
 for w in (1, 3):
-    for log2n in range(3, 27):
+    for log2n in [int(v) for v in os.environ["SWEEP_SIZES"].split(",")] if os.environ.get("SWEEP_SIZES") else range(3, 27):
         words = 1 << total_log
         n = 1 << log2n
         batch = max(1, words // (n * w))

@@ -66,6 +66,9 @@ namespace tf21 {
 #ifndef TF21_DFT_EXIT_MID
 #define TF21_DFT_EXIT_MID 0
 #endif
+#ifndef TF21_MID_DEFAULT_MASK
+#define TF21_MID_DEFAULT_MASK 0x1e0  /* K = 5 .. 8: measured faster than the thread-per-column passes they replace (ms per GiB of 2^15 / 16 / 17 / 18 / 26 / 27: 1.12 / 1.36 / 1.39 / 1.42 / 2.17 / 2.28 -> 1.06 / 1.09 / 1.21 / 1.28 / 1.90 / 2.08); K = 9 (32 elements per thread) is slower: 1.64 against 1.57 */
+#endif
 #ifndef TF21_FAST_COLS
 #define TF21_FAST_COLS 4  /* 4 CTAs of 128 threads per SM: finer interleaving of staging and compute phases than 2 x 256 (tools/ab.sh: 3.14 ms against 3.27 ms per 256-column batch once the staging is asynchronous; 32-byte row segments = one DRAM sector) */
 #endif
@@ -1100,6 +1103,103 @@ __global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt_col_n_kernel
     }
 }
 
+// ---- leading pass of 2^K points, 5 <= K <= 9, one CTA per [2^K rows][C word-columns] tile ----------------------------
+// K = A + B, A = ceil(K / 2).  256 threads; thread (c, g): c = tid % C (fastest: a warp instruction touches 32 / 16
+// consecutive words of one or two rows), g = tid / C < 2^B, C = 256 / 2^B.
+//   step 1: rows a 2^B + g (a < 2^A) of word-column c in registers: 2^A-point DFT over a (shift twiddles) -> k1,
+//           times omega_{2^K}^(k1 g), into shared memory s[(k1 2^B + g) C + c];
+//   step 2: thread (c, q) takes k1 = q + 2^B h (h < 2^(A-B)): 2^B-point DFT over g -> k2; row kappa = k1 + 2^A k2 gets the
+//           inter-pass twiddle and goes back to its own position (position preserving, like every leading pass).
+// Against the passes it replaces: one pass over the data instead of two thread-per-column passes of <= 32 points
+// (2^16 .. 2^19 and 2^26 .. 2^29), 8 .. 32 elements per thread instead of 32 .. 64 (more resident warps than the
+// warp-per-tile form ntt_col_n_kernel, which is latency bound), row segments of 128 .. 512 bytes.
+constexpr u32 kMidThreads = 256;
+// resident CTAs per SM the register allocation aims for: the pass is bound by the exposed latency of its one load phase
+// per CTA, so resident warps count for more than spill-free code (profiles/r02k_ab_mid_col_v4_resident_ctas.txt, ms per
+// GiB pass + row pass: 4 / 3 / 2 CTAs: 2^16 1.136, 2^17 1.241, 2^18 1.512; 5 / 4 / 3: 1.093, 1.209, 1.313; 6 / 5 / 4: 1.092,
+// 1.246, 1.283).  An L2 prefetch of a later tile's rows made it slower (+5 %, ..._v5_l2_prefetch.txt).
+#ifndef TF21_MID_BLOCKS_LO
+#define TF21_MID_BLOCKS_LO 5
+#endif
+#ifndef TF21_MID_BLOCKS_78
+#define TF21_MID_BLOCKS_78 4
+#endif
+#ifndef TF21_MID_OPT_CANON
+#define TF21_MID_OPT_CANON TF21_OPT_CANON
+#endif
+// whole warps only (every thread of the CTA is active): the optimistic stages of dft32_warp for any 2^A
+template <bool INV, int A>
+__device__ __forceinline__ void mid_dft(u64 (&v)[1 << A], u32 one) {
+#if TF21_MID_OPT_CANON
+    dft_opt_stage<INV, A, 1, TF21_SHL_WIDE>(v, one);
+#else
+    dft_pow2<INV, A>(v, one);
+#endif
+}
+template <int K>
+struct MidShape {
+    static constexpr int A = (K + 1) / 2, B = K - A, NA = 1 << A, NB = 1 << B, H = 1 << (A - B);
+    static constexpr u32 C = kMidThreads >> B;
+    static constexpr size_t smem = ((size_t)C << K) * sizeof(u64);
+};
+
+// (A persistent, double-buffered form -- the next tile arriving by 16-byte cp.async copies while the current one is
+// transformed in place -- measured slower: 1.28 against 1.14 ms per GiB at 2^16, profiles/r02k_ab_mid_col_v3_pipelined.txt;
+// the extra shared-memory round trip and the per-tile index arithmetic cost more than the exposed load latency of
+// four independent resident CTAs.)
+template <bool INV, int K>
+__global__ void __launch_bounds__(kMidThreads, (K <= 6 ? TF21_MID_BLOCKS_LO : K <= 8 ? TF21_MID_BLOCKS_78 : 3)) ntt_mid_col_kernel(const ColNArgs a) {
+    static_assert(K >= 3 && K <= 9, "leading passes of 8 .. 512 points");
+    using S = MidShape<K>;
+    constexpr int A = S::A, B = S::B, NA = S::NA, NB = S::NB, H = S::H;
+    constexpr u32 C = S::C;
+    extern __shared__ __align__(16) u64 smem[];
+    const u32 tid = threadIdx.x, c = tid % C, g = tid / C;
+    const u32 col = blockIdx.x * C + c;
+    const u32 o = blockIdx.y, b = blockIdx.z;
+    const u64 base = (u64)b * a.array_words + (u64)o * ((u64)a.inner_words << K) + col;
+    const u64 *src = a.src + base;
+    u64 *dst = a.dst + base;
+    u64 v[NA];
+#pragma unroll
+    for (int aa = 0; aa < NA; aa++) v[aa] = __ldcs(src + (u64)(aa * NB + (int)g) * a.inner_words);
+    const u32 one = (u32)__ldg(a.tw1);  // omega^0: an opaque 1 in a register (see gl_subp)
+    mid_dft<INV, A>(v, one);
+    {
+        const u64 *tw1 = a.tw1 + g;
+        u64 *sp = smem + g * C + c;
+#pragma unroll
+        for (int k1 = 0; k1 < NA; k1++) {
+            u64 x = v[brev_bits((u32)k1, A)];
+            if (k1 != 0) x = gl_mul(x, __ldg(tw1 + k1 * NB));
+            sp[(u32)k1 * NB * C] = x;
+        }
+    }
+    __syncthreads();
+    const u64 bmask = (1ull << a.log_b) - 1;
+    const u32 inner_elems = a.w == 1 ? a.inner_words : a.inner_words / 3u;
+    const u32 jrest = a.w == 1 ? col : col / 3u;
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        const u32 k1 = g + (u32)NB * (u32)h;
+        u64 z[NB];
+#pragma unroll
+        for (int gg = 0; gg < NB; gg++) z[gg] = smem[(k1 * NB + (u32)gg) * C + c];
+        mid_dft<INV, B>(z, one);
+#pragma unroll
+        for (int k2 = 0; k2 < NB; k2++) {
+            const u32 kappa = k1 + (u32)NA * (u32)k2;
+            u64 x = z[brev_bits((u32)k2, B)];
+            if (a.tw_full) {
+                x = gl_mul(x, __ldg(a.tw_full + (u64)kappa * inner_elems + jrest));
+            } else if (kappa != 0) {
+                x = gl_mul(x, scale_factor_l(a.tw, ((u64)kappa * jrest) & bmask));
+            }
+            __stcs(dst + (u64)kappa * a.inner_words, x);
+        }
+    }
+}
+
 // ---- n = 2^K < 1024: a warp takes 1024 consecutive elements = 2^(10-K) whole columns, all in registers ------
 // (reference benches at 2^7, benches/ntt.rs:19).  Flat element J of the batch = (array J / n, index J % n); a warp
 // owns J0 .. J0 + 1023 of one coefficient lane (w = 3: the three warps of a chunk interleave like the 2^10 kernel).
@@ -1219,6 +1319,34 @@ inline int get_col_n_tw1(DeviceTables &t, int dev, unsigned k, int inverse, cons
     u64 *d;
     TF21_TRY(upload(t, h, &d));
     g_col_n_tw1[key] = d;
+    *out = d;
+    return 0;
+}
+
+static std::map<std::tuple<int, unsigned, int>, u64 *> g_mid_tw1;  // (device, K, inverse), guarded by g_mutex
+
+// [2^A][2^B] omega_{2^K}^(+-k1 g) for ntt_mid_col_kernel<K>, K = A + B, A = ceil(K / 2)
+inline int get_mid_tw1(DeviceTables &t, int dev, unsigned k, int inverse, const u64 **out) {
+    auto key = std::make_tuple(dev, k, inverse);
+    auto it = g_mid_tw1.find(key);
+    if (it != g_mid_tw1.end()) {
+        *out = it->second;
+        return 0;
+    }
+    u64 w = hgl_root_of_unity(k);
+    if (inverse) w = hgl_inv(w);
+    const u32 la = (k + 1) / 2, lb = k - la;
+    std::vector<u64> h((size_t)1 << k);
+    for (u32 k1 = 0; k1 < (1u << la); k1++) {
+        u64 step = hgl_pow(w, k1), acc = 1;
+        for (u32 g = 0; g < (1u << lb); g++) {
+            h[(k1 << lb) + g] = acc;
+            acc = hgl_mul(acc, step);
+        }
+    }
+    u64 *d;
+    TF21_TRY(upload(t, h, &d));
+    g_mid_tw1[key] = d;
     *out = d;
     return 0;
 }
@@ -1359,6 +1487,15 @@ inline bool col_n_disabled() {
 inline bool col_n_forced() {
     static const bool on = getenv("TF21_COL_N_ALL") != nullptr;
     return on;
+}
+// TF21_MID_MASK: bit K set = the 2^K-point leading pass takes ntt_mid_col_kernel<K> (default: see kMidDefaultMask)
+constexpr u32 kMidDefaultMask = TF21_MID_DEFAULT_MASK;
+inline u32 mid_mask() {
+    static const u32 m = [] {
+        const char *e = getenv("TF21_MID_MASK");
+        return e ? (u32)strtoul(e, nullptr, 0) : kMidDefaultMask;
+    }();
+    return m;
 }
 inline bool small_n_disabled() {
     static const bool off = getenv("TF21_NO_SMALL_N") != nullptr;
@@ -1609,7 +1746,7 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
     u32 lead[3];
     u32 n_lead = 0;
     bool lead_is_col10[3] = {false, false, false};
-    bool first_is_coln = false;
+    bool first_is_coln = false, first_is_mid = false;
     {
         u32 rem = log_n - 10;
         const bool has_col = rem >= 10;
@@ -1624,6 +1761,10 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         // bound (4 warps per scheduler, 41 % issue, profiles/r02e_ncu_col_n_summary.txt) and loses 1 .. 15 %.
         first_is_coln = !prune_all && n_in == n && !pre.lo && !col_n_disabled() &&
                         ((rem >= 1 && rem <= 2) || (rem == 6 && has_col) || (col_n_forced() && rem >= 1 && rem <= 9));
+        // 32 .. 512 points in one pass through shared memory (ntt_mid_col_kernel) instead of two thread-per-column passes
+        first_is_mid = !prune_all && n_in == n && !pre.lo && rem >= 3 && rem <= 9 && ((mid_mask() >> rem) & 1u) &&
+                       !(col_n_forced() && first_is_coln) && ((((u64)1 << (log_n - rem)) * w) % (kMidThreads >> (rem / 2))) == 0;
+        if (first_is_mid) first_is_coln = true;  // same table and argument set-up as the register pass
         if (prune_all || first_is_coln) {
             lead[n_lead++] = rem;  // one pruned pass, or one register pass of 2^rem points (ntt_col_n_kernel)
         } else if (rem > 5) {  // 64-point columns per thread do not pay: ~200 KB of straight-line code, 196 registers
@@ -1691,6 +1832,51 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
             a.tw = tw;
             a.log_b = log_b;
             a.scaled = scalar % GL_P != 1 ? 1u : 0u;
+            if (first_is_mid) {
+                {
+                    std::lock_guard<std::mutex> lock(g_mutex);
+                    TF21_TRY(get_mid_tw1(tabs, dev, lp, inverse, &a.tw1));
+                }
+                // with a full table row 0 carries the scalar (or ones): every row is multiplied, nothing to flag
+                for (u64 b0 = 0; b0 < batch; b0 += 65535) {
+                    a.src = cur_src + b0 * array_words;
+                    a.dst = scratch + b0 * array_words;
+                    const unsigned nb = (unsigned)(batch - b0 < 65535 ? batch - b0 : 65535);
+#define TF21_MID_CASE(K_)                                                                                             \
+    case K_: {                                                                                                       \
+        const dim3 grid((unsigned)(inner_words / MidShape<K_>::C), n_outer, nb);                                     \
+        static std::once_flag once_f, once_i;                                                                        \
+        if (inverse) {                                                                                               \
+            std::call_once(once_i, [] {                                                                              \
+                cudaFuncSetAttribute(ntt_mid_col_kernel<true, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                     (int)MidShape<K_>::smem);                                                       \
+            });                                                                                                      \
+            TF21_LAUNCH_NAMED("ntt_mid_col_kernel", (ntt_mid_col_kernel<true, K_>), grid, kMidThreads,                \
+                              MidShape<K_>::smem, st, a);                                                            \
+        } else {                                                                                                     \
+            std::call_once(once_f, [] {                                                                              \
+                cudaFuncSetAttribute(ntt_mid_col_kernel<false, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     (int)MidShape<K_>::smem);                                                       \
+            });                                                                                                      \
+            TF21_LAUNCH_NAMED("ntt_mid_col_kernel", (ntt_mid_col_kernel<false, K_>), grid, kMidThreads,               \
+                              MidShape<K_>::smem, st, a);                                                            \
+        }                                                                                                            \
+        break;                                                                                                       \
+    }
+                    switch (lp) {
+                        TF21_MID_CASE(3) TF21_MID_CASE(4) TF21_MID_CASE(5) TF21_MID_CASE(6) TF21_MID_CASE(7) TF21_MID_CASE(8)
+                        TF21_MID_CASE(9)
+                        default: return TF21_E_BAD_ARG;
+                    }
+#undef TF21_MID_CASE
+                }
+                consumed += lp;
+                cur_src = scratch;
+                cur_src_words = array_words;
+                cur_n_in = n;
+                cur_pre = ScaleTab{nullptr, nullptr, 0};
+                continue;
+            }
             if (lp > 5) {
                 std::lock_guard<std::mutex> lock(g_mutex);
                 TF21_TRY(get_col_n_tw1(tabs, dev, lp, inverse, &a.tw1));

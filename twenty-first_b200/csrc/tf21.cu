@@ -320,6 +320,7 @@ int tf21_shutdown(void) {
     g_fast_tables.clear();  // their device pointers lived in `owned` and are gone: never hand them out again
     g_small_n_tw.clear();
     g_col_n_tw1.clear();
+    g_mid_tw1.clear();
     if (prev >= 0) cudaSetDevice(prev);
     return 0;
 }
