@@ -66,6 +66,12 @@ namespace tf21 {
 #ifndef TF21_DFT_EXIT_MID
 #define TF21_DFT_EXIT_MID 0
 #endif
+#ifndef TF21_SMALLCOL_BLOCKS
+#define TF21_SMALLCOL_BLOCKS 1
+#endif
+#ifndef TF21_PRUNED_BLOCKS
+#define TF21_PRUNED_BLOCKS 1
+#endif
 #ifndef TF21_MID_DEFAULT_MASK
 #define TF21_MID_DEFAULT_MASK 0x1e0  /* K = 5 .. 8: measured faster than the thread-per-column passes they replace (ms per GiB of 2^15 / 16 / 17 / 18 / 26 / 27: 1.12 / 1.36 / 1.39 / 1.42 / 2.17 / 2.28 -> 1.06 / 1.09 / 1.21 / 1.28 / 1.90 / 2.08); K = 9 (32 elements per thread) is slower: 1.64 against 1.57 */
 #endif
@@ -822,7 +828,7 @@ struct SmallColArgs {
 // columns, so every access is fully coalesced and nothing goes through shared memory); the whole
 // transform uses shift twiddles; then the inter-pass twiddle omega_B^(i * j_rest).
 template <bool INV, int A>
-__global__ void __launch_bounds__(128) ntt_small_col_kernel(const SmallColArgs a) {
+__global__ void __launch_bounds__(128, TF21_SMALLCOL_BLOCKS) ntt_small_col_kernel(const SmallColArgs a) {
     constexpr int NP = 1 << A;
     const u64 gid = (u64)blockIdx.x * 128 + threadIdx.x;
     const u64 q = gid % a.inner_words;
@@ -882,7 +888,7 @@ __constant__ u64 c_w64[64];
 // straight-line code and ran at 6.9 `no_instruction` stalls per issue (profiles/r02d_ncu_lde26_summary.txt);
 // the twiddles w^(a d) are now general products with a warp-uniform table entry.
 template <int A, int LNZ>
-__global__ void __launch_bounds__(128) ntt_small_col_pruned_kernel(const SmallColArgs a) {
+__global__ void __launch_bounds__(128, TF21_PRUNED_BLOCKS) ntt_small_col_pruned_kernel(const SmallColArgs a) {
     constexpr int NP = 1 << A, NZ = 1 << LNZ, M = NP / NZ;
     const u64 gid = (u64)blockIdx.x * 128 + threadIdx.x;
     const u64 q = gid % a.inner_words;
@@ -1027,7 +1033,7 @@ struct ColNArgs {
 };
 
 template <bool INV, int K>
-__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt_col_n_kernel(const ColNArgs a) {
+__global__ void __launch_bounds__(kFastThreads, (K <= 2 ? 5 : kFastMinBlocks)) ntt_col_n_kernel(const ColNArgs a) {
     static_assert(K >= 1 && K <= 9, "leading passes of 2 .. 512 points");
     constexpr u32 G = 1u << (10 - K);  // word-columns per warp
     extern __shared__ __align__(16) u64 smem[];
@@ -1217,7 +1223,9 @@ struct SmallNArgs {
 };
 
 template <bool INV, int K>
-__global__ void __launch_bounds__(kFastThreads, kFastMinBlocks) ntt_small_n_kernel(const SmallNArgs a) {
+// 5 resident CTAs (96 registers, 8 bytes of spill) for K = 6, 7: 2^6 0.707 -> 0.669 ms, 2^7 0.699 -> 0.610 ms per GiB; the other
+// sizes and the 2^10 single-pass kernel lose 1 .. 4 % with it (profiles/r02k_ab_min_blocks5_register_kernels.txt)
+__global__ void __launch_bounds__(kFastThreads, ((K == 6 || K == 7) ? 5 : kFastMinBlocks)) ntt_small_n_kernel(const SmallNArgs a) {
     static_assert(K >= 1 && K <= 9, "sizes below 2^10");
     extern __shared__ __align__(16) u64 smem[];
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
