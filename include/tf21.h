@@ -99,7 +99,11 @@ int tf21_selftest_tma_tile_dev(const uint64_t *d_matrix, uint64_t inner_words, u
 
 /* ---- NTT: math::ntt::ntt / intt (ntt.rs:67-82, 109-125) ------------------------------------- */
 /* In place over `batch` contiguous arrays of n*width words. n == 0 or 1 is a no-op.
- * out[i] = sum_j x[j] * omega_n^(i j), natural order in and out; intt also multiplies by n^-1.  */
+ * out[i] = sum_j x[j] * omega_n^(i j), natural order in and out; intt also multiplies by n^-1.
+ * Host memory: every entry point without a `_dev` suffix takes HOST pointers of any kind.  Pinned / registered
+ * memory is copied directly (both PCIe directions and the kernels overlapped); pageable memory -- a plain Vec or
+ * malloc block -- goes through the library's pinned staging ring (helper threads copy between the caller's slice
+ * and the ring; same results, about half the pinned rate instead of the driver's one-direction-at-a-time staging). */
 int tf21_ntt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch);
 int tf21_intt(uint64_t *data, uint64_t n, uint32_t width, uint64_t batch);
 int tf21_ntt_dev(uint64_t *d_data, uint64_t n, uint32_t width, uint64_t batch, int inverse,
