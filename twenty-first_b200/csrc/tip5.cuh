@@ -184,7 +184,9 @@ __device__ __forceinline__ void tip5_mds_sbox(u64 (&s)[TIP5_STATE], const uint8_
     }
 }
 
-template <int NVAR>
+// NOUT: only lanes 0 .. NOUT-1 of the result are needed (the last round of hash_10 / hash_pair feeds the digest, lanes
+// 0 .. 4, and nothing else: 5 of the 16 MDS outputs, tip5/mod.rs:583-585) -- the other outputs are left undefined.
+template <int NVAR, int NOUT = TIP5_STATE>
 __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *s_lut, const double *rc_lo,
                                            const double *rc_hi) {
     // ---- S-box ----
@@ -230,6 +232,7 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
         const double *rc = h ? rc_hi : rc_lo;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
+            if (i >= NOUT) continue;  // neither lane i nor lane i + 8 is needed
             double p = rc[i], q = rc[8 + i];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -241,6 +244,7 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
             }
 #pragma unroll
             for (int half = 0; half < 2; half++) {
+                if (i + 8 * half >= NOUT) continue;
                 const u64 acc = __double2ull_rn(half ? p - q : p + q);
                 if (h == 0) {
                     acc_l[i + 8 * half] = acc;
@@ -350,7 +354,10 @@ __device__ __forceinline__ void tip5_round(u64 (&s)[TIP5_STATE], const uint8_t *
 // split_and_lookup tip5/mod.rs:197-207; lanes 4..15 may be any representative mod p).
 // FIXED: lanes 10..15 are known to hold raw ONE (their contents are ignored).
 // On exit lanes 0..3 are canonical, lanes 4..15 weak; callers canonicalise what they store.
-template <bool FIXED = false>
+#ifndef TIP5_DIGEST_LAST
+#define TIP5_DIGEST_LAST 0  /* last round of the fixed-length hashes peeled, with only the five digest lanes of its MDS (-250 instructions of 7760 per hash): measured SLOWER, Merkle 2^24 5.57 against 5.34 ms, hash_10 3.07 against 3.19 G/s (profiles/r02k_ab_tip5_digest_only_last_round.txt) -- a third copy of the round in the instruction stream and 120 instead of 109 registers cost more than the 3 % of work saved */
+#endif
+template <bool FIXED = false, bool DIGEST_ONLY = false>
 __device__ __forceinline__ void tip5_permutation(u64 (&s)[TIP5_STATE], const uint8_t *s_lut) {
 #if TIP5_FUSED && TIP5_MDS_CRT
     // S-box(0) | MDS(0) + S-box(1) | ... | MDS(3) + S-box(4) | MDS(4)
@@ -366,9 +373,13 @@ __device__ __forceinline__ void tip5_permutation(u64 (&s)[TIP5_STATE], const uin
     return;
 #endif
     if (FIXED) tip5_round<TIP5_RATE>(s, s_lut, c_tip5_rc0f_lo, c_tip5_rc0f_hi);
+    constexpr int kLoopEnd = (DIGEST_ONLY && TIP5_DIGEST_LAST && TIP5_MDS_CRT && TIP5_MDS_SPLIT) ? TIP5_ROUNDS - 1 : TIP5_ROUNDS;
 #pragma unroll 1
-    for (int r = FIXED ? 1 : 0; r < TIP5_ROUNDS; r++)
+    for (int r = FIXED ? 1 : 0; r < kLoopEnd; r++)
         tip5_round<TIP5_STATE>(s, s_lut, c_tip5_rc_lo + r * TIP5_STATE, c_tip5_rc_hi + r * TIP5_STATE);
+    if (kLoopEnd < TIP5_ROUNDS)
+        tip5_round<TIP5_STATE, TIP5_DIGEST>(s, s_lut, c_tip5_rc_lo + (TIP5_ROUNDS - 1) * TIP5_STATE,
+                                            c_tip5_rc_hi + (TIP5_ROUNDS - 1) * TIP5_STATE);
 }
 
 // ---- cooperative form: 16 lanes per hash -----------------------------------------------------------------

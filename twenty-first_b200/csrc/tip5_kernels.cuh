@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kTip5Threads, TIP5_MIN_BLOCKS)
         s[2 * k + 1] = v.y;
         if (COPY) reinterpret_cast<ulonglong2 *>(copy_dst + 10 * i)[k] = v;
     }
-    tip5_permutation<true>(s, s_lut);  // capacity lanes = ONE, folded into the round-0 constants
+    tip5_permutation<true, true>(s, s_lut);  // capacity lanes = ONE, folded into the round-0 constants; digest lanes only
     u64 *dst = out + 5 * i;
 #pragma unroll
     for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
