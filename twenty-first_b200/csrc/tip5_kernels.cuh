@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(kTip5Threads) tip5_permute_kernel(u64 *__restr
     for (int k = 0; k < 8; k++) dst[k] = make_ulonglong2(gl_canon(s[2 * k]), gl_canon(s[2 * k + 1]));
 }
 
+#ifndef TIP5_HASH10_FIXED
+#define TIP5_HASH10_FIXED 1
+#endif
 // Tip5::hash_10 / hash_pair over a batch (tip5/mod.rs:559-586): state = in[0..10) | ONE x 6.
 // COPY: also store the 10 input words at copy_dst + 10 i -- the leaf level of the Merkle build, where the
 // reference copies the leaves into the node array (merkle_tree.rs:426) before hashing them.
@@ -147,7 +150,13 @@ __global__ void __launch_bounds__(kTip5Threads, TIP5_MIN_BLOCKS)
         s[2 * k + 1] = v.y;
         if (COPY) reinterpret_cast<ulonglong2 *>(copy_dst + 10 * i)[k] = v;
     }
+#if TIP5_HASH10_FIXED
     tip5_permutation<true, true>(s, s_lut);  // capacity lanes = ONE, folded into the round-0 constants; digest lanes only
+#else
+#pragma unroll
+    for (int k = TIP5_RATE; k < TIP5_STATE; k++) s[k] = TIP5_RAW_ONE;
+    tip5_permutation<false, true>(s, s_lut);  // one copy of the round in the instruction stream
+#endif
     u64 *dst = out + 5 * i;
 #pragma unroll
     for (int k = 0; k < TIP5_DIGEST; k++) dst[k] = gl_canon(s[k]);
