@@ -479,10 +479,13 @@ def test_concurrent_callers_are_thread_safe(tf, oracle):
     assert not errors, errors
 
 
-def test_ntt_four_pass_plan_2_27(tf, oracle):
-    """2^27 = 16 x 8 x 1024 x 1024 (two small passes + column pass + row pass): impulse response and
-    round trip (size-independent properties; the oracle would need minutes at this size)."""
-    n = 1 << 27
+@pytest.mark.parametrize("log2n", [27, 28])
+def test_ntt_four_pass_plan_2_27(tf, oracle, log2n):
+    """2^27 = 128 x 1024 x 1024 and 2^28 = 256 x 1024 x 1024 (one leading pass through shared memory, ntt_mid_col_kernel
+    with split twiddle tables, + column pass + row pass): impulse response and round trip (size-independent
+    properties; the oracle would need minutes at these sizes).  The host slice is one pageable array larger than a
+    staging chunk."""
+    n = 1 << log2n
     imp = np.zeros(n, dtype=np.uint64)
     imp[3] = 0xFFFFFFFF  # raw one at position 3 -> omega^(3 i)
     tf.ntt(imp)
