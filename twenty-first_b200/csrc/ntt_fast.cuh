@@ -73,7 +73,7 @@ namespace tf21 {
 #define TF21_PRUNED_BLOCKS 1
 #endif
 #ifndef TF21_MID_DEFAULT_MASK
-#define TF21_MID_DEFAULT_MASK 0x1e0  /* K = 5 .. 8: measured faster than the thread-per-column passes they replace (ms per GiB of 2^15 / 16 / 17 / 18 / 26 / 27: 1.12 / 1.36 / 1.39 / 1.42 / 2.17 / 2.28 -> 1.06 / 1.09 / 1.21 / 1.28 / 1.90 / 2.08); K = 9 (32 elements per thread) is slower: 1.64 against 1.57 */
+#define TF21_MID_DEFAULT_MASK 0x3e0  /* K = 5 .. 9: measured faster than the thread-per-column passes they replace (ms per GiB of 2^15 / 16 / 17 / 18 / 19 / 26 / 27: 1.12 / 1.36 / 1.39 / 1.42 / 1.63 / 2.17 / 2.28 -> 1.06 / 1.09 / 1.21 / 1.28 / 1.38 / 1.90 / 2.08); K = 9 is the two-thread form ntt_mid9_col_kernel (the generic form with 32 elements per thread is slower than the old passes: 1.64) */
 #endif
 #ifndef TF21_FAST_COLS
 #define TF21_FAST_COLS 4  /* 4 CTAs of 128 threads per SM: finer interleaving of staging and compute phases than 2 x 256 (tools/ab.sh: 3.14 ms against 3.27 ms per 256-column batch once the staging is asynchronous; 32-byte row segments = one DRAM sector) */
@@ -1206,6 +1206,110 @@ __global__ void __launch_bounds__(kMidThreads, (K <= 6 ? TF21_MID_BLOCKS_LO : K 
     }
 }
 
+// 512 points (K = 9) with 16 elements per thread: the 32 elements per thread of the generic form leave two resident
+// CTAs per SM (1.64 against 1.57 ms per GiB for the two thread-per-column passes it would replace).  Here 512 = 16 x 32:
+// step 1 as above (16-point transforms over a, times omega_512^(k1 g)); in step 2 the 32-point transform of a k1 is
+// shared by TWO threads -- thread h = 0 takes the even g, h = 1 the odd g (16-point transforms E, O), the odd side applies
+// omega_32^k (a shift twiddle), the halves change hands through the tile (one more barrier), and thread h forms
+// X[k + 16 h] = E[k] +- omega_32^k O[k].  Tile [512 rows][8 words] (64-byte row segments), 32 KB.
+// Generalised to K = 2 HB + 1 (HB = 4: 512 points, 16 elements per thread; HB = 3: 128 points, 8 elements per thread).
+template <int HB>
+struct Mid2Shape {
+    static constexpr int E = 1 << HB, NG = 2 << HB, K = 2 * HB + 1;
+    static constexpr u32 C = kMidThreads / NG;                       // word-columns per tile
+    static constexpr size_t smem = ((size_t)C << K) * sizeof(u64);  // [2^K rows][C]
+    static constexpr int EU = (39 << (6 - (HB + 1))) % 192;         // omega_NG = 2^EU
+};
+template <bool INV, int HB, int KK>
+__device__ __forceinline__ void mid2_combine(u64 (&z)[1 << HB], const u64 *part, u32 h, u32 one, u64 (&x)[1 << HB]) {
+    if constexpr (KK < (1 << HB)) {
+        // omega_NG^k = 2^(EU k); exponents >= 96 use 2^96 = -1 and swap sum and difference
+        constexpr int E0 = (Mid2Shape<HB>::EU * KK) % 192, E = INV ? (192 - E0) % 192 : E0;
+        constexpr bool neg = E >= 96;
+        const u64 mine = z[brev_bits((u32)KK, HB)], theirs = part[KK * Mid2Shape<HB>::C];
+        // h = 0 holds E[k] and reads the twiddled O[k]; h = 1 holds the twiddled O[k] and reads E[k]
+        const u64 e = h ? theirs : mine, o = h ? mine : theirs;
+        const bool add = (h == 0) != neg;
+        x[KK] = add ? gl_addl(e, o) : gl_subl(e, o, one);
+        mid2_combine<INV, HB, KK + 1>(z, part, h, one, x);
+    }
+}
+template <bool INV, int HB, int KK>
+__device__ __forceinline__ void mid2_twiddle_odd(u64 (&z)[1 << HB], u32 one) {
+    if constexpr (KK < (1 << HB)) {
+        constexpr int E0 = (Mid2Shape<HB>::EU * KK) % 192, E = INV ? (192 - E0) % 192 : E0;
+        constexpr int S = E >= 96 ? E - 96 : E;
+        u64 &r = z[brev_bits((u32)KK, HB)];
+        if constexpr (S == 0) r = gl_canonw(r);
+        else r = gl_shlc<(S ? S : 1)>(r, one);
+        mid2_twiddle_odd<INV, HB, KK + 1>(z, one);
+    }
+}
+#ifndef TF21_MID2_BLOCKS_7
+#define TF21_MID2_BLOCKS_7 5
+#endif
+template <bool INV, int HB>
+__global__ void __launch_bounds__(kMidThreads, (HB == 4 ? 4 : TF21_MID2_BLOCKS_7)) ntt_mid2_col_kernel(const ColNArgs a) {
+    using S = Mid2Shape<HB>;
+    constexpr int E = S::E, NG = S::NG, K = S::K;
+    constexpr u32 C = S::C;
+    extern __shared__ __align__(16) u64 smem[];
+    const u32 tid = threadIdx.x, c = tid % C, q = tid / C;  // q < NG
+    const u32 col = blockIdx.x * C + c;
+    const u32 o = blockIdx.y, b = blockIdx.z;
+    const u64 base = (u64)b * a.array_words + (u64)o * ((u64)a.inner_words << K) + col;
+    const u64 *src = a.src + base;
+    u64 *dst = a.dst + base;
+    const u32 one = (u32)__ldg(a.tw1);
+    u64 v[E];
+#pragma unroll
+    for (int aa = 0; aa < E; aa++) v[aa] = __ldcs(src + (u64)(aa * NG + (int)q) * a.inner_words);
+    mid_dft<INV, HB>(v, one);
+    {
+        const u64 *tw1 = a.tw1 + q;  // [E][NG]: omega_{2^K}^(k1 g)
+        u64 *sp = smem + q * C + c;
+#pragma unroll
+        for (int k1 = 0; k1 < E; k1++) {
+            u64 x = v[brev_bits((u32)k1, HB)];
+            if (k1 != 0) x = gl_mul(x, __ldg(tw1 + k1 * NG));
+            sp[(u32)k1 * NG * C] = x;
+        }
+    }
+    __syncthreads();
+    const u32 k1 = q & (u32)(E - 1), h = q >> HB;
+    u64 z[E];
+#pragma unroll
+    for (int gg = 0; gg < E; gg++) z[gg] = smem[(k1 * NG + 2 * (u32)gg + h) * C + c];
+    mid_dft<INV, HB>(z, one);
+    // the odd side carries omega_NG^k as a canonical word (an addend of the lazy sums); the even side's E[k] is only ever
+    // the first (lazy) operand
+    if (h) mid2_twiddle_odd<INV, HB, 0>(z, one);
+    __syncthreads();  // every thread has read its step-2 inputs: the tile can carry the halves
+    {
+        u64 *sp = smem + (k1 * NG + h * E) * C + c;
+#pragma unroll
+        for (int k = 0; k < E; k++) sp[(u32)k * C] = z[brev_bits((u32)k, HB)];
+    }
+    __syncthreads();
+    u64 x[E];
+    // the partner's value for index k sits at row k1 * NG + (1 - h) * E + k
+    mid2_combine<INV, HB, 0>(z, smem + (k1 * NG + (1u - h) * E) * C + c, h, one, x);
+    const u64 bmask = (1ull << a.log_b) - 1;
+    const u32 inner_elems = a.w == 1 ? a.inner_words : a.inner_words / 3u;
+    const u32 jrest = a.w == 1 ? col : col / 3u;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+        const u32 kappa = k1 + (u32)E * ((u32)k + (u32)E * h);
+        u64 y = x[k];
+        if (a.tw_full) {
+            y = gl_mul(y, __ldg(a.tw_full + (u64)kappa * inner_elems + jrest));
+        } else if (kappa != 0) {
+            y = gl_mul(y, scale_factor_l(a.tw, ((u64)kappa * jrest) & bmask));
+        }
+        __stcs(dst + (u64)kappa * a.inner_words, y);
+    }
+}
+
 // ---- n = 2^K < 1024: a warp takes 1024 consecutive elements = 2^(10-K) whole columns, all in registers ------
 // (reference benches at 2^7, benches/ntt.rs:19).  Flat element J of the batch = (array J / n, index J % n); a warp
 // owns J0 .. J0 + 1023 of one coefficient lane (w = 3: the three warps of a chunk interleave like the 2^10 kernel).
@@ -1334,8 +1438,8 @@ inline int get_col_n_tw1(DeviceTables &t, int dev, unsigned k, int inverse, cons
 static std::map<std::tuple<int, unsigned, int>, u64 *> g_mid_tw1;  // (device, K, inverse), guarded by g_mutex
 
 // [2^A][2^B] omega_{2^K}^(+-k1 g) for ntt_mid_col_kernel<K>, K = A + B, A = ceil(K / 2)
-inline int get_mid_tw1(DeviceTables &t, int dev, unsigned k, int inverse, const u64 **out) {
-    auto key = std::make_tuple(dev, k, inverse);
+inline int get_mid_tw1(DeviceTables &t, int dev, unsigned k, int inverse, const u64 **out, unsigned la_override = 0) {
+    auto key = std::make_tuple(dev, k + 100 * la_override, inverse);
     auto it = g_mid_tw1.find(key);
     if (it != g_mid_tw1.end()) {
         *out = it->second;
@@ -1343,7 +1447,7 @@ inline int get_mid_tw1(DeviceTables &t, int dev, unsigned k, int inverse, const 
     }
     u64 w = hgl_root_of_unity(k);
     if (inverse) w = hgl_inv(w);
-    const u32 la = (k + 1) / 2, lb = k - la;
+    const u32 la = la_override ? la_override : (k + 1) / 2, lb = k - la;
     std::vector<u64> h((size_t)1 << k);
     for (u32 k1 = 0; k1 < (1u << la); k1++) {
         u64 step = hgl_pow(w, k1), acc = 1;
@@ -1504,6 +1608,18 @@ inline u32 mid_mask() {
         return e ? (u32)strtoul(e, nullptr, 0) : kMidDefaultMask;
     }();
     return m;
+}
+#ifndef TF21_MID7_TWO_THREAD
+#define TF21_MID7_TWO_THREAD 1  /* 2^17: 1.211 -> 1.175 ms per GiB, 2^27: 2.055 -> 2.005 (profiles/r02l_ab_mid7_two_thread.txt) */
+#endif
+// 128 points: the two-thread form (8 elements per thread) instead of the generic one (16); TF21_MID7_TWO_THREAD in the
+// environment overrides the default for A/B runs
+inline bool mid7_two_thread() {
+    static const bool v = [] {
+        const char *e = getenv("TF21_MID7_TWO_THREAD");
+        return e ? e[0] == '1' : (bool)TF21_MID7_TWO_THREAD;
+    }();
+    return v;
 }
 inline bool small_n_disabled() {
     static const bool off = getenv("TF21_NO_SMALL_N") != nullptr;
@@ -1771,7 +1887,7 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
                         ((rem >= 1 && rem <= 2) || (rem == 6 && has_col) || (col_n_forced() && rem >= 1 && rem <= 9));
         // 32 .. 512 points in one pass through shared memory (ntt_mid_col_kernel) instead of two thread-per-column passes
         first_is_mid = !prune_all && n_in == n && !pre.lo && rem >= 3 && rem <= 9 && ((mid_mask() >> rem) & 1u) &&
-                       !(col_n_forced() && first_is_coln) && ((((u64)1 << (log_n - rem)) * w) % (kMidThreads >> (rem / 2))) == 0;
+                       !(col_n_forced() && first_is_coln) && ((((u64)1 << (log_n - rem)) * w) % (rem == 9 ? 8u : (kMidThreads >> (rem / 2)))) == 0;
         if (first_is_mid) first_is_coln = true;  // same table and argument set-up as the register pass
         if (prune_all || first_is_coln) {
             lead[n_lead++] = rem;  // one pruned pass, or one register pass of 2^rem points (ntt_col_n_kernel)
@@ -1843,7 +1959,7 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
             if (first_is_mid) {
                 {
                     std::lock_guard<std::mutex> lock(g_mutex);
-                    TF21_TRY(get_mid_tw1(tabs, dev, lp, inverse, &a.tw1));
+                    TF21_TRY(get_mid_tw1(tabs, dev, lp, inverse, &a.tw1, lp == 9 ? 4u : (lp == 7 && mid7_two_thread()) ? 3u : 0u));
                 }
                 // with a full table row 0 carries the scalar (or ones): every row is multiplied, nothing to flag
                 for (u64 b0 = 0; b0 < batch; b0 += 65535) {
@@ -1872,8 +1988,30 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         break;                                                                                                       \
     }
                     switch (lp) {
-                        TF21_MID_CASE(3) TF21_MID_CASE(4) TF21_MID_CASE(5) TF21_MID_CASE(6) TF21_MID_CASE(7) TF21_MID_CASE(8)
-                        TF21_MID_CASE(9)
+                        TF21_MID_CASE(3) TF21_MID_CASE(4) TF21_MID_CASE(5) TF21_MID_CASE(6) TF21_MID_CASE(8)
+                        case 7: {
+                            if (mid7_two_thread()) {
+                                const dim3 grid((unsigned)(inner_words / Mid2Shape<3>::C), n_outer, nb);
+                                if (inverse)
+                                    TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<true, 3>), grid, kMidThreads, Mid2Shape<3>::smem, st, a);
+                                else
+                                    TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<false, 3>), grid, kMidThreads, Mid2Shape<3>::smem, st, a);
+                                break;
+                            }
+                            switch (lp) {
+                                TF21_MID_CASE(7)
+                                default: break;
+                            }
+                            break;
+                        }
+                        case 9: {
+                            const dim3 grid((unsigned)(inner_words / Mid2Shape<4>::C), n_outer, nb);
+                            if (inverse)
+                                TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<true, 4>), grid, kMidThreads, Mid2Shape<4>::smem, st, a);
+                            else
+                                TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<false, 4>), grid, kMidThreads, Mid2Shape<4>::smem, st, a);
+                            break;
+                        }
                         default: return TF21_E_BAD_ARG;
                     }
 #undef TF21_MID_CASE
