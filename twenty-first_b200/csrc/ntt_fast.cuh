@@ -1249,7 +1249,7 @@ __device__ __forceinline__ void mid2_twiddle_odd(u64 (&z)[1 << HB], u32 one) {
 #define TF21_MID2_BLOCKS_7 5
 #endif
 template <bool INV, int HB>
-__global__ void __launch_bounds__(kMidThreads, (HB == 4 ? 4 : TF21_MID2_BLOCKS_7)) ntt_mid2_col_kernel(const ColNArgs a) {
+__global__ void __launch_bounds__(kMidThreads, (HB == 4 ? 4 : HB == 3 ? TF21_MID2_BLOCKS_7 : 6)) ntt_mid2_col_kernel(const ColNArgs a) {
     using S = Mid2Shape<HB>;
     constexpr int E = S::E, NG = S::NG, K = S::K;
     constexpr u32 C = S::C;
@@ -1609,17 +1609,16 @@ inline u32 mid_mask() {
     }();
     return m;
 }
-#ifndef TF21_MID7_TWO_THREAD
-#define TF21_MID7_TWO_THREAD 1  /* 2^17: 1.211 -> 1.175 ms per GiB, 2^27: 2.055 -> 2.005 (profiles/r02l_ab_mid7_two_thread.txt) */
+#ifndef TF21_MID2_DEFAULT_MASK
+#define TF21_MID2_DEFAULT_MASK 0x280  /* bit K set: the 2^K-point leading pass (odd K) takes the two-thread form ntt_mid2_col_kernel: K = 9 (2^19: 1.63 -> 1.38 ms per GiB) and K = 7 (2^17: 1.211 -> 1.175, 2^27: 2.055 -> 2.005; profiles/r02l_ab_mid7_two_thread.txt) */
 #endif
-// 128 points: the two-thread form (8 elements per thread) instead of the generic one (16); TF21_MID7_TWO_THREAD in the
-// environment overrides the default for A/B runs
-inline bool mid7_two_thread() {
-    static const bool v = [] {
-        const char *e = getenv("TF21_MID7_TWO_THREAD");
-        return e ? e[0] == '1' : (bool)TF21_MID7_TWO_THREAD;
+// TF21_MID2_MASK in the environment overrides the default for A/B runs
+inline bool mid_two_thread(u32 k) {
+    static const u32 m = [] {
+        const char *e = getenv("TF21_MID2_MASK");
+        return e ? (u32)strtoul(e, nullptr, 0) : (u32)TF21_MID2_DEFAULT_MASK;
     }();
-    return v;
+    return (k == 5 || k == 7 || k == 9) && ((m >> k) & 1u);
 }
 inline bool small_n_disabled() {
     static const bool off = getenv("TF21_NO_SMALL_N") != nullptr;
@@ -1887,7 +1886,7 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
                         ((rem >= 1 && rem <= 2) || (rem == 6 && has_col) || (col_n_forced() && rem >= 1 && rem <= 9));
         // 32 .. 512 points in one pass through shared memory (ntt_mid_col_kernel) instead of two thread-per-column passes
         first_is_mid = !prune_all && n_in == n && !pre.lo && rem >= 3 && rem <= 9 && ((mid_mask() >> rem) & 1u) &&
-                       !(col_n_forced() && first_is_coln) && ((((u64)1 << (log_n - rem)) * w) % (rem == 9 ? 8u : (kMidThreads >> (rem / 2)))) == 0;
+                       !(col_n_forced() && first_is_coln) && ((((u64)1 << (log_n - rem)) * w) % (kMidThreads >> (rem / 2))) == 0 && (rem != 9 || mid_two_thread(9));
         if (first_is_mid) first_is_coln = true;  // same table and argument set-up as the register pass
         if (prune_all || first_is_coln) {
             lead[n_lead++] = rem;  // one pruned pass, or one register pass of 2^rem points (ntt_col_n_kernel)
@@ -1959,7 +1958,7 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
             if (first_is_mid) {
                 {
                     std::lock_guard<std::mutex> lock(g_mutex);
-                    TF21_TRY(get_mid_tw1(tabs, dev, lp, inverse, &a.tw1, lp == 9 ? 4u : (lp == 7 && mid7_two_thread()) ? 3u : 0u));
+                    TF21_TRY(get_mid_tw1(tabs, dev, lp, inverse, &a.tw1, mid_two_thread(lp) ? (lp - 1) / 2 : 0u));
                 }
                 // with a full table row 0 carries the scalar (or ones): every row is multiplied, nothing to flag
                 for (u64 b0 = 0; b0 < batch; b0 += 65535) {
@@ -1987,31 +1986,26 @@ inline int ntt_run(DeviceTables &tabs, int dev, const u64 *src, u64 n_in, u64 *d
         }                                                                                                            \
         break;                                                                                                       \
     }
+#define TF21_MID2_CASE(HB_)                                                                                           \
+    {                                                                                                                \
+        const dim3 grid((unsigned)(inner_words / Mid2Shape<HB_>::C), n_outer, nb);                                   \
+        if (inverse)                                                                                                 \
+            TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<true, HB_>), grid, kMidThreads,             \
+                              Mid2Shape<HB_>::smem, st, a);                                                          \
+        else                                                                                                         \
+            TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<false, HB_>), grid, kMidThreads,            \
+                              Mid2Shape<HB_>::smem, st, a);                                                          \
+        continue;                                                                                                    \
+    }
+                    if (mid_two_thread(lp)) {
+                        if (lp == 5) TF21_MID2_CASE(2)
+                        if (lp == 7) TF21_MID2_CASE(3)
+                        TF21_MID2_CASE(4)
+                    }
+#undef TF21_MID2_CASE
                     switch (lp) {
-                        TF21_MID_CASE(3) TF21_MID_CASE(4) TF21_MID_CASE(5) TF21_MID_CASE(6) TF21_MID_CASE(8)
-                        case 7: {
-                            if (mid7_two_thread()) {
-                                const dim3 grid((unsigned)(inner_words / Mid2Shape<3>::C), n_outer, nb);
-                                if (inverse)
-                                    TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<true, 3>), grid, kMidThreads, Mid2Shape<3>::smem, st, a);
-                                else
-                                    TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<false, 3>), grid, kMidThreads, Mid2Shape<3>::smem, st, a);
-                                break;
-                            }
-                            switch (lp) {
-                                TF21_MID_CASE(7)
-                                default: break;
-                            }
-                            break;
-                        }
-                        case 9: {
-                            const dim3 grid((unsigned)(inner_words / Mid2Shape<4>::C), n_outer, nb);
-                            if (inverse)
-                                TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<true, 4>), grid, kMidThreads, Mid2Shape<4>::smem, st, a);
-                            else
-                                TF21_LAUNCH_NAMED("ntt_mid2_col_kernel", (ntt_mid2_col_kernel<false, 4>), grid, kMidThreads, Mid2Shape<4>::smem, st, a);
-                            break;
-                        }
+                        TF21_MID_CASE(3) TF21_MID_CASE(4) TF21_MID_CASE(5) TF21_MID_CASE(6) TF21_MID_CASE(7) TF21_MID_CASE(8)
+                        TF21_MID_CASE(9)
                         default: return TF21_E_BAD_ARG;
                     }
 #undef TF21_MID_CASE
