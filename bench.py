@@ -514,6 +514,37 @@ def main():
                            "api": "tf21_ntt / tf21_intt (host pointers, pageable memory, pinned staging ring)"}
         del pg
 
+    # ---- Merkle e2e: host leaves in, host node array out, through tf21_merkle_build (N = 1 only: it is a per-process call) --
+    merkle_e2e = None
+    if not args.no_e2e and world == 1:
+        h_leafs = torch.empty(5 * n_leafs, dtype=torch.int64).pin_memory()
+        h_leafs.copy_(leafs)
+        h_nodes = torch.empty(10 * n_leafs, dtype=torch.int64).pin_memory()
+        ln, nn = h_leafs.numpy().view(np.uint64), h_nodes.numpy().view(np.uint64)
+        B = importlib.import_module("twenty-first_b200._binding")
+        import ctypes
+
+        def host_build(a, b):
+            B.check(B.lib.tf21_merkle_build(ctypes.c_void_p(a.ctypes.data), n_leafs, ctypes.c_void_p(b.ctypes.data)))
+
+        host_build(ln, nn)
+        t0 = time.perf_counter()
+        host_build(ln, nn)
+        pin_s = time.perf_counter() - t0
+        root_ok = bool(np.array_equal(nn[5:10], nodes[5:10].cpu().numpy().view(np.uint64)))
+        pl, pn = np.array(ln), np.empty_like(nn)
+        host_build(pl, pn)
+        t0 = time.perf_counter()
+        host_build(pl, pn)
+        pg_s = time.perf_counter() - t0
+        merkle_e2e = {"value": n_leafs / pin_s, "unit": "leaves/s", "api": "tf21_merkle_build (host pointers, pinned)",
+                      "h2d_bytes": 40 * n_leafs, "d2h_bytes": 40 * n_leafs,
+                      "note": "the leaf half of the node array is copied on the host, only inner nodes cross PCIe",
+                      "root_equals_device_build": root_ok,
+                      "pageable": {"value": n_leafs / pg_s, "unit": "leaves/s",
+                                   "nodes_equal_pinned_run": bool(np.array_equal(pn, nn))}}
+        del h_leafs, h_nodes, pl, pn
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_leg(2, 1, args.cpu_cols or args.cols, 22)
@@ -545,7 +576,7 @@ def main():
                          "dominant_kernel": dominant[0],
                          "per_kernel_ms_avg": {k: t / c for k, (t, c) in ntt_agg.items()}},
             "merkle": {"value": leaves_per_s, "unit": "leaves/s", "ms_per_step": merkle_ms / args.steps,
-                       "leaves_per_gpu": n_leafs, "n_rank_root_parity": merkle_parity,
+                       "leaves_per_gpu": n_leafs, "n_rank_root_parity": merkle_parity, "e2e": merkle_e2e,
                        "roofline": {"bound": "hbm", "achieved": merkle_achieved, "peak": peak_gbs, "unit": "GB/s",
                                     "frac": merkle_achieved / peak_gbs,
                                     "traffic": traffic_of("tip5_hash10_kernel", f"merkle{args.merkle_log2}"),
