@@ -52,20 +52,49 @@ __device__ __forceinline__ void eis_dft8(Eis (&v)[8]) {
     eis_bfly<0>(v[0], v[1]); eis_bfly<EU>(v[4], v[5]); eis_bfly<2 * EU>(v[2], v[3]); eis_bfly<3 * EU>(v[6], v[7]);
 }
 
-// bit 0: integer DFT8 (dft_pow2<false, 3>), bit 1: FP64 DFT8, on independent data of the same thread
+// lazy u64 word -> (lo32, hi32) as exact doubles: the 2^52-bias trick, one DADD per component, no XU conversion
+__device__ __forceinline__ Eis eis_from_u64(u64 x) {
+    const double B52 = 4503599627370496.0;
+    return Eis{__hiloint2double(0x43300000, (int)(u32)x) - B52, __hiloint2double(0x43300000, (int)(u32)(x >> 32)) - B52};
+}
+// a + b * 2^32 (|a|, |b| < 2^48) -> a lazy u64 representative mod p.  Both components are made non-negative with an offset of
+// 2^48 (value + 2^48 + 2^80, and 2^80 = 2^48 - 2^16 mod p: the constant C = 2^49 - 2^16 is subtracted at the end); the
+// biased doubles a' + 2^52, b' + 2^52 carry the integers in their low 52 bits:
+//   a' + b' 2^32 = alo + (ahi + blo) 2^32 + bhi 2^64 = (blo : alo) + [((ahi + bhi) << 32) - bhi]   (2^64 = 2^32 - 1)
+__device__ __forceinline__ u64 eis_to_u64(Eis e, u32 one) {
+    const double OFF = 281474976710656.0 + 4503599627370496.0;  // 2^48 + 2^52
+    const u64 ab = (u64)__double_as_longlong(e.a + OFF), bb = (u64)__double_as_longlong(e.b + OFF);
+    const u32 alo = (u32)ab, ahi = (u32)(ab >> 32) & 0xFFFFFu, blo = (u32)bb, bhi = (u32)(bb >> 32) & 0xFFFFFu;
+    const u64 T = ((u64)(ahi + bhi) << 32) - bhi;
+    const u64 v = gl_addl(gl_pack(alo, blo), T);
+    return gl_subl(v, 0x0001FFFFFFFF0000ull, one);
+}
+
+// bit 0: integer DFT8 (dft_pow2<false, 3>), bit 1: FP64 DFT8, on independent data of the same thread;
+// bit 2: the FP64 side starts from and returns to lazy u64 words every round (conversions included)
 template <int OP>
 __global__ void __launch_bounds__(128) k(const u64 *in, u64 *out) {
     const u32 t = threadIdx.x + blockIdx.x * blockDim.x;
-    u64 v[8];
+    u64 v[8], w[8];
     Eis e[8];
+    const u32 one = (u32)(in[1023] >> 63) + 1u - (u32)(in[1023] >> 63);  // 1, opaque enough for this tool
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         const u64 x = in[(t + c * 977) & 1023];
         v[c] = x;
+        w[c] = x ^ 0x5555;
         e[c] = Eis{(double)(u32)x, (double)(u32)(x >> 32)};
     }
     for (int it = 0; it < ITERS; it++) {
         if (OP & 1) dft_pow2<false, 3>(v);
+        if (OP & 4) {
+            Eis f[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) f[c] = eis_from_u64(w[c]);
+            eis_dft8(f);
+#pragma unroll
+            for (int c = 0; c < 8; c++) w[c] = eis_to_u64(f[c], one);
+        }
         if (OP & 2) {
             eis_dft8(e);
 #pragma unroll
@@ -77,7 +106,7 @@ __global__ void __launch_bounds__(128) k(const u64 *in, u64 *out) {
     }
     u64 acc = 0;
 #pragma unroll
-    for (int c = 0; c < 8; c++) acc ^= v[c] ^ (u64)(long long)e[c].a ^ ((u64)(long long)e[c].b << 7);
+    for (int c = 0; c < 8; c++) acc ^= v[c] ^ w[c] ^ (u64)(long long)e[c].a ^ ((u64)(long long)e[c].b << 7);
     out[t] = acc;
 }
 
@@ -95,6 +124,9 @@ __global__ void check(const u64 *in, u64 *out) {
         out[c] = gl_canon(v[c]);
         out[8 + c] = (u64)(long long)e[c].a;
         out[16 + c] = (u64)(long long)e[c].b;
+        out[24 + c] = gl_canon(eis_to_u64(e[c], 1u));
+        const Eis r = eis_from_u64(in[c]);
+        out[32 + c] = gl_canon(eis_to_u64(r, 1u)) ^ gl_canon(in[c]);  // 0 when the conversions round-trip
     }
 }
 
@@ -130,7 +162,7 @@ int main() {
     }
     cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
     check<<<1, 1>>>(in, out);
-    u64 r[24];
+    u64 r[40];
     cudaMemcpy(r, out, sizeof(r), cudaMemcpyDeviceToHost);
     int ok = 1;
     for (int c = 0; c < 8; c++) {
@@ -139,10 +171,13 @@ int main() {
         __int128 m = val % (__int128)GL_P;
         if (m < 0) m += (__int128)GL_P;
         if ((u64)m != r[c]) ok = 0;
+        if (r[24 + c] != r[c] || r[32 + c] != 0) ok = 0;  // back to a u64 word: same field element
     }
-    printf("FP64 Eisenstein DFT8 equals the integer DFT8 mod p: %s\n", ok ? "yes" : "NO");
+    printf("FP64 Eisenstein DFT8 (and its way back to u64 words) equals the integer DFT8 mod p: %s\n", ok ? "yes" : "NO");
     run<1>("integer DFT8 (product code)", in, out, sms, 0);
     run<2>("FP64 DFT8 (a + b phi)", in, out, sms, 0);
     run<3>("both, independent data, one stream", in, out, sms, 0);
+    run<4>("FP64 DFT8 from / to u64 words", in, out, sms, 0);
+    run<5>("integer DFT8 + FP64 DFT8 from / to u64", in, out, sms, 0);
     return ok ? 0 : 1;
 }
