@@ -66,11 +66,18 @@ namespace tf21 {
 #ifndef TF21_DFT_EXIT_MID
 #define TF21_DFT_EXIT_MID 0
 #endif
-#ifndef TF21_SMALLCOL_BLOCKS
-#define TF21_SMALLCOL_BLOCKS 1
+// A/B knobs for the resident-CTA target of the thread-per-column passes (profiles/r02k_ab_occupancy_small_col_pruned.txt: no
+// gain); unset = plain __launch_bounds__(128) -- a minimum of ONE block is not the same thing to ptxas: it then spends up
+// to 150 registers on these kernels (2^14: 0.98 -> 1.005 ms per GiB, pruned pass 0.50 -> 0.53 ms)
+#ifdef TF21_SMALLCOL_BLOCKS
+#define TF21_SMALLCOL_BOUNDS __launch_bounds__(128, TF21_SMALLCOL_BLOCKS)
+#else
+#define TF21_SMALLCOL_BOUNDS __launch_bounds__(128)
 #endif
-#ifndef TF21_PRUNED_BLOCKS
-#define TF21_PRUNED_BLOCKS 1
+#ifdef TF21_PRUNED_BLOCKS
+#define TF21_PRUNED_BOUNDS __launch_bounds__(128, TF21_PRUNED_BLOCKS)
+#else
+#define TF21_PRUNED_BOUNDS __launch_bounds__(128)
 #endif
 #ifndef TF21_MID_DEFAULT_MASK
 #define TF21_MID_DEFAULT_MASK 0x3e0  /* K = 5 .. 9: measured faster than the thread-per-column passes they replace (ms per GiB of 2^15 / 16 / 17 / 18 / 19 / 26 / 27: 1.12 / 1.36 / 1.39 / 1.42 / 1.63 / 2.17 / 2.28 -> 1.06 / 1.09 / 1.21 / 1.28 / 1.38 / 1.90 / 2.08); K = 9 is the two-thread form ntt_mid9_col_kernel (the generic form with 32 elements per thread is slower than the old passes: 1.64) */
@@ -828,7 +835,7 @@ struct SmallColArgs {
 // columns, so every access is fully coalesced and nothing goes through shared memory); the whole
 // transform uses shift twiddles; then the inter-pass twiddle omega_B^(i * j_rest).
 template <bool INV, int A>
-__global__ void __launch_bounds__(128, TF21_SMALLCOL_BLOCKS) ntt_small_col_kernel(const SmallColArgs a) {
+__global__ void TF21_SMALLCOL_BOUNDS ntt_small_col_kernel(const SmallColArgs a) {
     constexpr int NP = 1 << A;
     const u64 gid = (u64)blockIdx.x * 128 + threadIdx.x;
     const u64 q = gid % a.inner_words;
@@ -888,7 +895,7 @@ __constant__ u64 c_w64[64];
 // straight-line code and ran at 6.9 `no_instruction` stalls per issue (profiles/r02d_ncu_lde26_summary.txt);
 // the twiddles w^(a d) are now general products with a warp-uniform table entry.
 template <int A, int LNZ>
-__global__ void __launch_bounds__(128, TF21_PRUNED_BLOCKS) ntt_small_col_pruned_kernel(const SmallColArgs a) {
+__global__ void TF21_PRUNED_BOUNDS ntt_small_col_pruned_kernel(const SmallColArgs a) {
     constexpr int NP = 1 << A, NZ = 1 << LNZ, M = NP / NZ;
     const u64 gid = (u64)blockIdx.x * 128 + threadIdx.x;
     const u64 q = gid % a.inner_words;
