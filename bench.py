@@ -52,8 +52,9 @@ class ClockSampler:
         self.stop = threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
 
-    def _run_nvml(self) -> bool:
-        """fast path: NVML in-process (a sample every ~2 ms, so that even a 50 ms timed region is covered)"""
+    def _init_nvml(self):
+        """NVML is initialised on the calling thread BEFORE the timed region (nvmlInit alone can take 100 ms and more:
+        a sampler that initialises inside its thread misses most of a 0.2 s region)"""
         try:
             import pynvml as nv
 
@@ -65,8 +66,17 @@ class ClockSampler:
             bits = [("nvmlClocksThrottleReasonHwSlowdown", 0x8), ("nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                     ("nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), ("nvmlClocksThrottleReasonSwPowerCap", 0x4)]
             masks = [getattr(nv, name, default) for name, default in bits]
+            get_reasons(h)  # first call of each entry point done here
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self._nvml = (nv, h, mx, get_reasons, masks)
         except Exception:
+            self._nvml = None
+
+    def _run_nvml(self) -> bool:
+        """fast path: NVML in-process (a sample every ~2 ms, so that even a 50 ms timed region is covered)"""
+        if self._nvml is None:
             return False
+        nv, h, mx, get_reasons, masks = self._nvml
         while not self.stop.is_set():
             try:
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
@@ -92,6 +102,7 @@ class ClockSampler:
             self.stop.wait(0.05)
 
     def __enter__(self):
+        self._init_nvml()
         self.thread.start()
         return self
 
